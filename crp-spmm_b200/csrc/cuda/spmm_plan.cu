@@ -1,0 +1,126 @@
+// spmm_plan.cu - SpMM plan (device CSR) management and kernel dispatch.
+// crp_cuda_spmm_plan_create / _exec / _destroy stand where the reference calls
+// mkl_sparse_d_create_csr / mkl_sparse_d_mm / mkl_sparse_destroy
+// (src/rowpara_spmm.c:398-408) - but the handle is built once at init, not per exec.
+#include <cstring>
+#include <vector>
+
+#include "crp_cuda_internal.cuh"
+
+template <typename T, int VECN>
+void crp_launch_rowsplit(
+    const crp_spmm_plan *plan, const T *val, const int n, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
+    T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
+);
+
+extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint)
+{
+    crp_spmm_plan *p = (crp_spmm_plan *) calloc(1, sizeof(crp_spmm_plan));
+    p->m = m;
+    p->k = k;
+    p->nnz = (m > 0) ? (long long) rowptr_h[m] - rowptr_h[0] : 0;
+    p->n_hint = n_hint;
+    p->variant = CRP_VARIANT_AUTO;
+    p->last_kernel = "none";
+    if (m > 0 && rowptr_h[0] != 0) { fprintf(stderr, "[FATAL] crp_cuda_spmm_plan_create: rowptr must be 0-based\n"); abort(); }
+    int mx = 0;
+    for (int i = 0; i < m; i++) { const int d = rowptr_h[i + 1] - rowptr_h[i]; if (d > mx) mx = d; }
+    p->max_row_nnz = mx;
+    p->avg_row_nnz = (m > 0) ? (double) p->nnz / m : 0.0;
+    CRP_CUDA_CHECK(cudaMalloc((void **) &p->d_rowptr, sizeof(int) * ((size_t) m + 1)));
+    if (m > 0) CRP_CUDA_CHECK(cudaMemcpy(p->d_rowptr, rowptr_h, sizeof(int) * ((size_t) m + 1), cudaMemcpyHostToDevice));
+    else CRP_CUDA_CHECK(cudaMemset(p->d_rowptr, 0, sizeof(int)));
+    if (p->nnz > 0)
+    {
+        CRP_CUDA_CHECK(cudaMalloc((void **) &p->d_colidx, sizeof(int) * (size_t) p->nnz));
+        CRP_CUDA_CHECK(cudaMalloc((void **) &p->d_val, sizeof(double) * (size_t) p->nnz));
+        CRP_CUDA_CHECK(cudaMemcpy(p->d_colidx, colidx_h, sizeof(int) * (size_t) p->nnz, cudaMemcpyHostToDevice));
+        CRP_CUDA_CHECK(cudaMemcpy(p->d_val, val_h, sizeof(double) * (size_t) p->nnz, cudaMemcpyHostToDevice));
+    }
+    return p;
+}
+
+extern "C" void crp_cuda_spmm_plan_destroy(crp_spmm_plan *plan)
+{
+    if (plan == NULL) return;
+    if (plan->d_rowptr) CRP_CUDA_CHECK(cudaFree(plan->d_rowptr));
+    if (plan->d_colidx) CRP_CUDA_CHECK(cudaFree(plan->d_colidx));
+    if (plan->d_val)    CRP_CUDA_CHECK(cudaFree(plan->d_val));
+    if (plan->d_val32)  CRP_CUDA_CHECK(cudaFree(plan->d_val32));
+    if (plan->d_mp_rowstart) CRP_CUDA_CHECK(cudaFree(plan->d_mp_rowstart));
+    free(plan);
+}
+
+__global__ void __launch_bounds__(256) cast_f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+        dst[i] = (float) src[i];
+}
+
+static void ensure_val32(crp_spmm_plan *plan, cudaStream_t stream)
+{
+    if (plan->d_val32 != NULL || plan->nnz == 0) return;
+    CRP_CUDA_CHECK(cudaMalloc((void **) &plan->d_val32, sizeof(float) * (size_t) plan->nnz));
+    size_t blocks = ((size_t) plan->nnz + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cast_f64_to_f32_kernel<<<(unsigned) blocks, 256, 0, stream>>>(plan->d_val, plan->d_val32, (size_t) plan->nnz);
+    CRP_LAUNCH_CHECK();
+}
+
+extern "C" void crp_cuda_spmm_exec(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
+    const void *X0, const int ldx0, const int x0_rows, const void *X1, const int ldx1,
+    const double beta, void *C, const int ldc, void *stream
+)
+{
+    if (plan == NULL) { fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: NULL plan\n"); abort(); }
+    if (plan->m == 0 || n <= 0) return;
+    cudaStream_t s = as_stream(stream);
+    if (elem_size == 8)
+    {
+        plan->last_kernel = "spmm_rowsplit_f64";
+        crp_launch_rowsplit<double, 2>(plan, plan->d_val, n, (const double *) X0, (size_t) ldx0, x0_rows, (const double *) X1, (size_t) ldx1,
+                                       alpha, beta, (double *) C, (size_t) ldc, s);
+    } else if (elem_size == 4) {
+        ensure_val32(plan, s);
+        plan->last_kernel = "spmm_rowsplit_f32";
+        crp_launch_rowsplit<float, 4>(plan, plan->d_val32, n, (const float *) X0, (size_t) ldx0, x0_rows, (const float *) X1, (size_t) ldx1,
+                                      (float) alpha, (float) beta, (float *) C, (size_t) ldc, s);
+    } else {
+        fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: elem_size must be 4 or 8\n");
+        abort();
+    }
+}
+
+extern "C" const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan) { return plan ? plan->last_kernel : "none"; }
+
+extern "C" void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name)
+{
+    if (plan == NULL || name == NULL) return;
+    if (strcmp(name, "rowsplit") == 0) plan->variant = CRP_VARIANT_ROWSPLIT;
+    else if (strcmp(name, "rowblock") == 0) plan->variant = CRP_VARIANT_ROWBLOCK;
+    else if (strcmp(name, "mergepath") == 0) plan->variant = CRP_VARIANT_MERGEPATH;
+    else plan->variant = CRP_VARIANT_AUTO;
+}
+
+extern "C" void crp_cuda_csr_spmm_host(
+    const int m, const int n, const int k, const double alpha,
+    const int A_nnz, const int *A_rowptr_h, const int *A_colidx_h, const double *A_val_h,
+    const double *B_h, const int ldB, const double beta, double *C_h, const int ldC
+)
+{
+    (void) A_nnz;
+    crp_spmm_plan *plan = crp_cuda_spmm_plan_create(m, k, A_rowptr_h, A_colidx_h, A_val_h, n);
+    double *B_d = NULL, *C_d = NULL;
+    const size_t row_bytes = sizeof(double) * (size_t) n;
+    CRP_CUDA_CHECK(cudaMalloc((void **) &B_d, row_bytes * (size_t) (k > 0 ? k : 1)));
+    CRP_CUDA_CHECK(cudaMalloc((void **) &C_d, row_bytes * (size_t) (m > 0 ? m : 1)));
+    if (k > 0 && n > 0) CRP_CUDA_CHECK(cudaMemcpy2D(B_d, row_bytes, B_h, sizeof(double) * (size_t) ldB, row_bytes, (size_t) k, cudaMemcpyHostToDevice));
+    if (beta != 0.0 && m > 0 && n > 0) CRP_CUDA_CHECK(cudaMemcpy2D(C_d, row_bytes, C_h, sizeof(double) * (size_t) ldC, row_bytes, (size_t) m, cudaMemcpyHostToDevice));
+    crp_cuda_spmm_exec(plan, n, 8, alpha, B_d, n, k, NULL, 0, beta, C_d, n, NULL);
+    CRP_CUDA_CHECK(cudaStreamSynchronize(0));
+    if (m > 0 && n > 0) CRP_CUDA_CHECK(cudaMemcpy2D(C_h, sizeof(double) * (size_t) ldC, C_d, row_bytes, row_bytes, (size_t) m, cudaMemcpyDeviceToHost));
+    CRP_CUDA_CHECK(cudaFree(B_d));
+    CRP_CUDA_CHECK(cudaFree(C_d));
+    crp_cuda_spmm_plan_destroy(plan);
+}

@@ -1,0 +1,101 @@
+/*
+ * crp_common.c - process-wide options, device binding and the pinned-buffer cache.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "utils.h"
+#include "crp_ext.h"
+#include "crp_internal.h"
+
+static void *g_user_stream = NULL;
+static int   g_blocking = 1;
+static int   g_dev_state = -1;      /* -1 unknown, 0 no device (plan-only), 1 bound */
+
+const char *crp_version(void) { return "crpspmm-b200 0.1 (sm_100a, NCCL data plane)"; }
+
+void crp_set_stream(void *stream) { g_user_stream = stream; }
+void crp_set_blocking(const int blocking) { g_blocking = blocking ? 1 : 0; }
+void *crp_opt_stream(void) { return g_user_stream; }
+int crp_opt_blocking(void) { return g_blocking; }
+
+int crp_opt_plan_only(void)
+{
+    int v;
+    GET_ENV_INT_VAR(v, "CRP_SPMM_PLAN_ONLY", "plan_only", 0, 0, 1, 0);
+    return v;
+}
+
+int crp_opt_pin_host(void)
+{
+    static int v = -1;
+    if (v < 0) GET_ENV_INT_VAR(v, "CRP_SPMM_PIN_HOST", "pin_host", 1, 0, 1, 0);
+    return v;
+}
+
+int crp_device_ready(void)
+{
+    if (g_dev_state >= 0) return g_dev_state;
+    if (crp_opt_plan_only())
+    {
+        g_dev_state = 0;
+        return 0;
+    }
+    if (crp_cuda_device_count() <= 0)
+    {
+        fprintf(stderr,
+            "[FATAL] CRP-SpMM (B200 build): no CUDA device is visible and there is no CPU fallback.\n"
+            "        (Host-side planning alone can be exercised with CRP_SPMM_PLAN_ONLY=1.)\n");
+        fflush(stderr);
+        abort();
+    }
+    crp_cuda_select_device_by_local_rank();
+    g_dev_state = 1;
+    return 1;
+}
+
+/* ---- pinned caller buffers ---- */
+typedef struct { const char *ptr; size_t bytes; } pin_entry;
+static pin_entry g_pins[64];
+static int g_npin = 0;
+
+void crp_pin_host_range(const void *ptr, size_t bytes)
+{
+    if (!crp_opt_pin_host() || ptr == NULL || bytes < ((size_t) 1 << 20)) return;
+    const char *p = (const char *) ptr;
+    for (int i = 0; i < g_npin; i++)
+        if (p >= g_pins[i].ptr && p + bytes <= g_pins[i].ptr + g_pins[i].bytes) return;
+    /* an overlapping but different range (e.g. realloc'd buffer): drop the stale registration first */
+    for (int i = 0; i < g_npin; i++)
+    {
+        if (p < g_pins[i].ptr + g_pins[i].bytes && g_pins[i].ptr < p + bytes)
+        {
+            crp_cuda_host_unregister(g_pins[i].ptr);
+            g_pins[i] = g_pins[--g_npin];
+            i--;
+        }
+    }
+    if (g_npin == (int) (sizeof(g_pins) / sizeof(g_pins[0])))
+    {
+        crp_cuda_host_unregister(g_pins[0].ptr);
+        memmove(&g_pins[0], &g_pins[1], sizeof(pin_entry) * (size_t) (g_npin - 1));
+        g_npin--;
+    }
+    if (crp_cuda_host_register(ptr, bytes))
+    {
+        g_pins[g_npin].ptr = p;
+        g_pins[g_npin].bytes = bytes;
+        g_npin++;
+    }
+}
+
+int *crp_comm_ranks_in_parent(MPI_Comm sub, MPI_Comm parent)
+{
+    int n, mine;
+    MPI_Comm_size(sub, &n);
+    MPI_Comm_rank(parent, &mine);
+    int *tab = (int *) malloc(sizeof(int) * (size_t) n);
+    MPI_Allgather(&mine, 1, MPI_INT, tab, 1, MPI_INT, sub);
+    return tab;
+}

@@ -1,0 +1,84 @@
+/*
+ * crp_internal.h - declarations shared by the host sources of libcrpspmm.
+ * Nothing here is part of the public surface.
+ */
+#ifndef CRP_INTERNAL_H
+#define CRP_INTERNAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <mpi.h>
+
+#include "crp_cuda.h"
+#include "rowpara_spmm.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- process-wide options (crp_common.c) ---- */
+void *crp_opt_stream(void);          /* caller-provided stream or NULL               */
+int   crp_opt_blocking(void);        /* 1: exec returns after completion (default)   */
+int   crp_opt_plan_only(void);       /* CRP_SPMM_PLAN_ONLY=1: host plans only        */
+int   crp_opt_pin_host(void);        /* CRP_SPMM_PIN_HOST (default 1): register host B / C buffers */
+/* Binds this process to "its" GPU on first use (local rank % #GPUs); aborts when
+ * there is no GPU unless plan-only mode was requested.  Returns 1 if a device is in use. */
+int   crp_device_ready(void);
+
+/* cache of pinned (cudaHostRegister'ed) caller buffers, so that repeated execs on the
+ * same host B / C run their PCIe copies at full speed */
+void  crp_pin_host_range(const void *ptr, size_t bytes);
+
+/* ---- NCCL layer (comm/crp_nccl.c) ---- */
+typedef struct crp_nccl_comm crp_nccl_comm;
+/* Communicator spanning exactly the ranks of `comm` (cached by membership; collective over comm). */
+crp_nccl_comm *crp_nccl_get(MPI_Comm comm);
+int   crp_nccl_rank(const crp_nccl_comm *nc);
+int   crp_nccl_size(const crp_nccl_comm *nc);
+void  crp_nccl_group_start(void);
+void  crp_nccl_group_end(void);
+void  crp_nccl_send(crp_nccl_comm *nc, const void *buf, size_t bytes, int peer, void *stream);
+void  crp_nccl_recv(crp_nccl_comm *nc, void *buf, size_t bytes, int peer, void *stream);
+void  crp_nccl_shutdown(void);
+
+/* rank of every member of `sub` inside `parent` (malloc'd, size of sub); collective over sub */
+int  *crp_comm_ranks_in_parent(MPI_Comm sub, MPI_Comm parent);
+
+/* ---- device-side state of a row-parallel engine (rowpara_spmm.c) ---- */
+struct crp_rp_dev
+{
+    crp_spmm_plan *plan;        /* device CSR with "virtual" column ids (see rp_build_device_state) */
+    int     nB;                 /* B rows owned by this rank                                         */
+    int     n_send_rows;        /* rows packed per exec                                              */
+    int     n_recv_rows;        /* remote rows received per exec                                     */
+    int     *d_sridxs;          /* device copy of rB_sridxs                                          */
+    void    *d_sendbuf;  size_t sendbuf_bytes;
+    void    *d_recvbuf;  size_t recvbuf_bytes;
+    void    *d_Bwork;    size_t Bwork_bytes;   /* row-major device copy of B when the caller's is host / column-major */
+    void    *d_Cwork;    size_t Cwork_bytes;
+    void    *d_Lwork;    size_t Lwork_bytes;   /* column-major staging for host + BC_layout = 1      */
+    void    *stream;            /* own non-blocking stream                                           */
+    void    *ev[5];             /* start, packed, exchanged, multiplied, end                         */
+    int     pending;            /* events of the last exec not yet folded into the statistics        */
+    void    *pending_stream;
+    double  pending_host_t0;
+    crp_nccl_comm *nc;          /* NCCL communicator used for the B-row exchange                     */
+    int     *peer_nc_rank;      /* nproc: rank of each member of rp->comm inside nc                  */
+};
+
+/* rp_spmm_init with an explicit NCCL parent: the exchange runs on the NCCL
+ * communicator of `nccl_parent` (collective over it must be possible for all its
+ * members at this point) instead of one created for `comm`. */
+void rp_spmm_init_on(
+    const int A_srow, const int A_nrow, const int *A_rowptr, const int *A_colidx,
+    const double *A_val, const int *B_row_displs, const int glb_n, MPI_Comm comm,
+    MPI_Comm nccl_parent, rp_spmm_p *rp_spmm
+);
+
+void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const int ldB, void *C, const int ldC, const int elem_size);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,130 @@
+/*
+ * crp_cuda.h - the thin C-ABI CUDA layer under the CRP-SpMM host code.
+ *
+ * Successor of the reference's (deprecated, host-only) CUDA proxy
+ * deprecated/src/cuda_proxy.h:13-66: plain C linkage, plain pointers and sizes,
+ * void returns, abort-on-error (like CUDA_RUNTIME_CHECK, deprecated/src/cuda_utils.h:23-34).
+ * Where the proxy wrapped cudaMemcpy2D and one cusparseSpMM call, this layer
+ * owns hand-written sm_100a kernels.  Entry point -> what it replaces:
+ *   crp_cuda_select_device_by_local_rank <- select_cuda_device_by_mpi_local_rank  cuda_proxy.cu:38-46
+ *   crp_cuda_set_device                  <- cuda_set_rt_dev_id                    cuda_proxy.cu:48-51
+ *   crp_cuda_memcpy_{h2d,d2h,d2d,auto}   <- cuda_memcpy_*                         cuda_proxy.cu:53-72
+ *   crp_cuda_malloc_{dev,host}, free_*   <- cuda_malloc_*, cuda_free_*            cuda_proxy.cu:74-97
+ *   crp_cuda_memset_dev                  <- cuda_memset_dev
+ *   crp_cuda_device_sync / stream_sync   <- cuda_device_sync / cuda_stream_sync   cuda_proxy.cu:99-106
+ *   crp_cuda_copy_matrix                 <- cuda_copy_matrix (cudaMemcpy2D)       cuda_proxy.cu:108-118
+ *   crp_cuda_csr_spmm_host               <- cuda_cusparse_csr_spmm                cuda_proxy.cu:122-182
+ *   crp_cuda_spmm_plan_* / spmm_exec     <- mkl_sparse_d_create_csr / _mm / _destroy at src/rowpara_spmm.c:398-408
+ *   crp_cuda_gather_rows                 <- the OpenMP pack loop                  src/rowpara_spmm.c:232-262
+ *   crp_cuda_copy_blocks                 <- the per-block dev_type_copy_matrix loops src/mat_redist.c:327-348, 395-416
+ *   crp_cuda_transpose                   <- (new) column-major <-> row-major staging for BC_layout = 1
+ * `stream` arguments are cudaStream_t passed as void* (NULL = the legacy default stream).
+ */
+#ifndef CRPSPMM_CRP_CUDA_H
+#define CRPSPMM_CRP_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device management ---- */
+int  crp_cuda_device_count(void);                 /* 0 when no driver / no GPU; never aborts       */
+void crp_cuda_select_device_by_local_rank(void);  /* MINIMPI_LOCAL_RANK / LOCAL_RANK / ... % #GPUs  */
+void crp_cuda_set_device(const int dev_id);
+int  crp_cuda_get_device(void);
+int  crp_cuda_sm_count(void);
+int  crp_cuda_ptr_is_device(const void *ptr);     /* 1 if ptr is device (or managed) memory         */
+
+/* ---- memory ---- */
+void crp_cuda_malloc_dev(void **dptr_, const size_t bytes);
+void crp_cuda_malloc_host(void **hptr_, const size_t bytes);   /* pinned */
+void crp_cuda_free_dev(void *dptr);
+void crp_cuda_free_host(void *hptr);
+void crp_cuda_memset_dev(void *dptr, const int value, const size_t bytes);
+void crp_cuda_memcpy_h2d(const void *hptr, void *dptr, const size_t bytes);
+void crp_cuda_memcpy_d2h(const void *dptr, void *hptr, const size_t bytes);
+void crp_cuda_memcpy_d2d(const void *dptr_src, void *dptr_dst, const size_t bytes);
+void crp_cuda_memcpy_auto(const void *src, void *dst, const size_t bytes);
+void crp_cuda_memcpy_async(const void *src, void *dst, const size_t bytes, void *stream);
+/* strided host<->device / device<->device copy of nrow rows of row_bytes bytes (cudaMemcpy2DAsync) */
+void crp_cuda_memcpy2d_async(const void *src, size_t src_pitch, void *dst, size_t dst_pitch, size_t row_bytes, size_t nrow, void *stream);
+/* pin an existing host range so async copies from / to it run at full PCIe speed; returns 1 on success */
+int  crp_cuda_host_register(const void *hptr, const size_t bytes);
+void crp_cuda_host_unregister(const void *hptr);
+
+/* ---- streams and events ---- */
+void  crp_cuda_device_sync(void);
+void  crp_cuda_stream_sync(void *stream);
+void *crp_cuda_stream_create(void);               /* non-blocking stream */
+void  crp_cuda_stream_destroy(void *stream);
+void *crp_cuda_event_create(void);
+void  crp_cuda_event_destroy(void *event);
+void  crp_cuda_event_record(void *event, void *stream);
+void  crp_cuda_event_sync(void *event);
+void  crp_cuda_stream_wait_event(void *stream, void *event);
+float crp_cuda_event_elapsed_ms(void *start, void *stop);
+
+/* ---- data-movement kernels (all row-major, element size 4 or 8 unless noted) ---- */
+
+/* dst[0:nrow, 0:ncol] := src[0:nrow, 0:ncol]; blocking like the reference proxy */
+void crp_cuda_copy_matrix(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, void *dst, const int ldd);
+void crp_cuda_copy_matrix_async(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, void *dst, const int ldd, void *stream);
+
+/* dst[i, 0:ncol] := src[ridx[i], 0:ncol], i < nrow; ridx is a device array */
+void crp_cuda_gather_rows(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, const int *ridx_d, void *dst, const int ldd, void *stream);
+
+/* one launch copying a list of rectangular byte blocks (device array of descriptors) */
+typedef struct
+{
+    uint64_t src_off;     /* byte offset of the block's first element from src_base */
+    uint64_t dst_off;     /* byte offset from dst_base                              */
+    uint64_t src_pitch;   /* bytes between consecutive rows in the source           */
+    uint64_t dst_pitch;   /* bytes between consecutive rows in the destination      */
+    uint32_t nrow;        /* rows                                                   */
+    uint32_t row_bytes;   /* bytes per row                                          */
+} crp_copy_block;
+void crp_cuda_copy_blocks(const crp_copy_block *blocks_d, const int nblk, const void *src_base, void *dst_base, void *stream);
+
+/* dst (ncol x nrow, leading dimension ldd) := transpose of src (nrow x ncol, leading dimension lds) */
+void crp_cuda_transpose(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, void *dst, const int ldd, void *stream);
+
+/* ---- local SpMM ---- */
+typedef struct crp_spmm_plan crp_spmm_plan;
+
+/* Upload a 0-based CSR matrix (host arrays; m rows, column indices < k) and
+ * prepare whatever auxiliary structures the kernels want.  n_hint is the
+ * expected dense width (0 = unknown). */
+crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint);
+void crp_cuda_spmm_plan_destroy(crp_spmm_plan *plan);
+
+/* C (m x n, row-major, ldc) := alpha * A * X + beta * C   (beta == 0: C is not read).
+ * X is the row-major matrix whose rows [0, x0_rows) live in X0 (leading dimension ldx0)
+ * and rows >= x0_rows in X1 (leading dimension ldx1, row r at X1 + (r - x0_rows) * ldx1);
+ * pass x0_rows >= k and X1 = NULL for a single piece.
+ * elem_size 8: X, C are fp64.  elem_size 4: X, C are fp32 and A's values are used as fp32. */
+void crp_cuda_spmm_exec(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
+    const void *X0, const int ldx0, const int x0_rows, const void *X1, const int ldx1,
+    const double beta, void *C, const int ldc, void *stream
+);
+/* name of the kernel variant the last crp_cuda_spmm_exec on this plan launched (static string) */
+const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan);
+/* force a kernel variant for experiments: "auto", "rowsplit", "rowblock", "mergepath" */
+void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name);
+
+/* Host-in / host-out convenience with the deprecated proxy's argument list:
+ * C_h := alpha * A * B_h + beta * C_h, everything on the host, row-major fp64. */
+void crp_cuda_csr_spmm_host(
+    const int m, const int n, const int k, const double alpha,
+    const int A_nnz, const int *A_rowptr_h, const int *A_colidx_h, const double *A_val_h,
+    const double *B_h, const int ldB, const double beta, double *C_h, const int ldC
+);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,47 @@
+/*
+ * crp_ext.h - additions of the B200 build that have no counterpart in the
+ * reference API.  Existing callers never need them; bench.py and the fp32
+ * configuration (BASELINE.json config 5) do.
+ */
+#ifndef CRPSPMM_CRP_EXT_H
+#define CRPSPMM_CRP_EXT_H
+
+#include "rowpara_spmm.h"
+#include "para2d_spmm.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* fp32 B and C (A's values are rounded to fp32 once, on the device).  Same rules as the fp64 calls. */
+void rp_spmm_exec_f32(rp_spmm_p rp_spmm, const int BC_layout, const float *B, const int ldB, float *C, const int ldC);
+void para2d_spmm_exec_f32(para2d_spmm_p para2d_spmm, const int BC_layout, const float *B, const int ldB, float *C, const int ldC);
+
+/* By default every engine launches on its own non-blocking stream and exec
+ * returns after the result is complete (reference semantics).  A caller that
+ * manages streams itself can (a) make all engines created afterwards launch on
+ * `stream` (a cudaStream_t; NULL restores the default) and (b) drop the final
+ * synchronisation so that exec only enqueues work. */
+void crp_set_stream(void *stream);
+void crp_set_blocking(const int blocking);
+
+/* Number of kernels launched / NCCL groups issued by this process since start. */
+unsigned long long crp_kernel_launch_count(void);
+unsigned long long crp_nccl_group_count(void);
+
+/* Name of the local-SpMM kernel variant the engine's last exec launched. */
+const char *rp_spmm_kernel_name(rp_spmm_p rp_spmm);
+/* Force a variant ("auto", "rowsplit", "rowblock", "mergepath") for experiments. */
+void rp_spmm_set_kernel(rp_spmm_p rp_spmm, const char *name);
+
+/* 1 if the engine was created in plan-only mode (CRP_SPMM_PLAN_ONLY=1, no device state). */
+int rp_spmm_is_plan_only(rp_spmm_p rp_spmm);
+
+/* Library version string. */
+const char *crp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
