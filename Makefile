@@ -1,0 +1,82 @@
+# Build of the B200-native CRP-SpMM library (sm_100a only).
+#
+#   make            libminimpi.so, minimpirun, libcrpspmm.so           -> crp-spmm_b200/{lib,bin}
+#   make drivers    the reference's example drivers, compiled UNCHANGED from $(REF)/examples
+#                   against include/ + libcrpspmm.so (only where $(REF) exists)
+#   make oracle     oracle/liboracle.so and, where $(REF) exists, oracle/_ref/*
+#   make clean
+REF     ?= /root/reference
+ROOT    := $(abspath $(dir $(lastword $(MAKEFILE_LIST))))
+PKG     := $(ROOT)/crp-spmm_b200
+SRC     := $(PKG)/csrc
+LIBDIR  := $(PKG)/lib
+BINDIR  := $(PKG)/bin
+OBJDIR  := $(ROOT)/build/obj
+MINIMPI := $(PKG)/minimpi
+
+CC      ?= gcc
+NVCC    ?= nvcc
+CFLAGS  := -O2 -g -std=gnu11 -fPIC -fopenmp -Wall -Wno-unused-function -I$(ROOT)/include -I$(MINIMPI) -I$(SRC)/host -I/usr/local/cuda/include
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function \
+           -I$(ROOT)/include -I$(SRC)/cuda $(CRP_NVCC_EXTRA)
+
+HOST_SRC := utils.c spmat_part.c dev_type.c crp_common.c rowpara_spmm.c para2d_spmm.c mat_redist.c
+COMM_SRC := crp_nccl.c
+CUDA_SRC := $(notdir $(wildcard $(SRC)/cuda/*.cu))
+OBJS := $(addprefix $(OBJDIR)/host_,$(HOST_SRC:.c=.o)) $(addprefix $(OBJDIR)/comm_,$(COMM_SRC:.c=.o)) $(addprefix $(OBJDIR)/cuda_,$(CUDA_SRC:.cu=.o))
+
+.PHONY: all lib drivers oracle clean
+all: lib
+
+lib: $(LIBDIR)/libminimpi.so $(BINDIR)/minimpirun $(LIBDIR)/libcrpspmm.so
+
+$(OBJDIR) $(LIBDIR) $(BINDIR):
+	mkdir -p $@
+
+$(LIBDIR)/libminimpi.so: $(MINIMPI)/minimpi.c $(MINIMPI)/mpi.h | $(LIBDIR)
+	$(CC) -O2 -g -fPIC -shared -o $@ $<
+
+$(BINDIR)/minimpirun: $(MINIMPI)/minimpirun.c | $(BINDIR)
+	$(CC) -O2 -o $@ $<
+
+$(OBJDIR)/host_%.o: $(SRC)/host/%.c $(wildcard $(ROOT)/include/*.h) $(SRC)/host/crp_internal.h | $(OBJDIR)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(OBJDIR)/comm_%.o: $(SRC)/comm/%.c $(wildcard $(ROOT)/include/*.h) $(SRC)/host/crp_internal.h | $(OBJDIR)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(OBJDIR)/cuda_%.o: $(SRC)/cuda/%.cu $(wildcard $(SRC)/cuda/*.cuh) $(ROOT)/include/crp_cuda.h | $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIBDIR)/libcrpspmm.so: $(OBJS) $(LIBDIR)/libminimpi.so
+	$(NVCC) -shared -o $@ $(OBJS) -L$(LIBDIR) -lminimpi -ldl -lgomp -Xlinker -rpath='$$ORIGIN'
+
+# ---- the reference's own drivers against this library (drop-in check) ----
+DRV_INC  := -I$(ROOT)/include -I$(MINIMPI) -I$(ROOT)/oracle/stubs -I$(REF)/examples
+DRV_HELP := mmio.c mmio_utils.c test_utils.c metis_mat_part.c
+DRV_OBJS := $(addprefix $(OBJDIR)/drv_,$(DRV_HELP:.c=.o)) $(OBJDIR)/drv_mkl_standin.o $(OBJDIR)/drv_metis_stub.o
+DRV_CFLAGS := -O3 -march=x86-64-v3 -fopenmp -std=gnu11 -g -DUSE_MKL -Wno-unused-result
+
+ifneq ($(wildcard $(REF)/examples/test_para2d_spmm.c),)
+drivers: lib $(BINDIR)/test_para2d_spmm.exe $(BINDIR)/test_rp_spmm.exe $(BINDIR)/test_spmm_2dpg.exe
+else
+drivers:
+	@echo "drivers: $(REF) not present - keeping prebuilt drivers (if any)"
+endif
+
+$(OBJDIR)/drv_%.o: $(REF)/examples/%.c | $(OBJDIR)
+	$(CC) $(DRV_CFLAGS) $(DRV_INC) -c $< -o $@
+$(OBJDIR)/drv_mkl_standin.o: $(ROOT)/oracle/stubs/mkl_standin.c | $(OBJDIR)
+	$(CC) $(DRV_CFLAGS) -ffp-contract=off $(DRV_INC) -c $< -o $@
+$(OBJDIR)/drv_metis_stub.o: $(ROOT)/oracle/stubs/metis_stub.c | $(OBJDIR)
+	$(CC) $(DRV_CFLAGS) $(DRV_INC) -c $< -o $@
+
+$(BINDIR)/%.exe: $(OBJDIR)/drv_%.o $(DRV_OBJS) $(LIBDIR)/libcrpspmm.so | $(BINDIR)
+	$(CC) -fopenmp -o $@ $< $(DRV_OBJS) -L$(LIBDIR) -lcrpspmm -lminimpi -lm -Wl,-rpath,'$$ORIGIN/../lib'
+
+oracle:
+	$(MAKE) -C $(ROOT)/oracle all
+
+clean:
+	rm -rf $(ROOT)/build $(LIBDIR) $(BINDIR)
+.SECONDARY:

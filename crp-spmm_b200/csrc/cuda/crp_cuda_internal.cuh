@@ -35,6 +35,7 @@ enum { CRP_VARIANT_AUTO = 0, CRP_VARIANT_ROWSPLIT = 1, CRP_VARIANT_ROWBLOCK = 2,
 struct crp_spmm_plan
 {
     int       m, k;
+    int       x0_rows;          // X rows [0, x0_rows) come from X0, the rest from X1
     long long nnz;
     int       n_hint;
     int       variant;          // CRP_VARIANT_*

@@ -13,11 +13,12 @@ void crp_launch_rowsplit(
     T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
 );
 
-extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint)
+extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int x0_rows, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint)
 {
     crp_spmm_plan *p = (crp_spmm_plan *) calloc(1, sizeof(crp_spmm_plan));
     p->m = m;
     p->k = k;
+    p->x0_rows = (x0_rows > k) ? k : x0_rows;
     p->nnz = (m > 0) ? (long long) rowptr_h[m] - rowptr_h[0] : 0;
     p->n_hint = n_hint;
     p->variant = CRP_VARIANT_AUTO;
@@ -69,10 +70,11 @@ static void ensure_val32(crp_spmm_plan *plan, cudaStream_t stream)
 
 extern "C" void crp_cuda_spmm_exec(
     crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
-    const void *X0, const int ldx0, const int x0_rows, const void *X1, const int ldx1,
+    const void *X0, const int ldx0, const void *X1, const int ldx1,
     const double beta, void *C, const int ldc, void *stream
 )
 {
+    const int x0_rows = plan ? plan->x0_rows : 0;
     if (plan == NULL) { fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: NULL plan\n"); abort(); }
     if (plan->m == 0 || n <= 0) return;
     cudaStream_t s = as_stream(stream);
@@ -110,14 +112,14 @@ extern "C" void crp_cuda_csr_spmm_host(
 )
 {
     (void) A_nnz;
-    crp_spmm_plan *plan = crp_cuda_spmm_plan_create(m, k, A_rowptr_h, A_colidx_h, A_val_h, n);
+    crp_spmm_plan *plan = crp_cuda_spmm_plan_create(m, k, k, A_rowptr_h, A_colidx_h, A_val_h, n);
     double *B_d = NULL, *C_d = NULL;
     const size_t row_bytes = sizeof(double) * (size_t) n;
     CRP_CUDA_CHECK(cudaMalloc((void **) &B_d, row_bytes * (size_t) (k > 0 ? k : 1)));
     CRP_CUDA_CHECK(cudaMalloc((void **) &C_d, row_bytes * (size_t) (m > 0 ? m : 1)));
     if (k > 0 && n > 0) CRP_CUDA_CHECK(cudaMemcpy2D(B_d, row_bytes, B_h, sizeof(double) * (size_t) ldB, row_bytes, (size_t) k, cudaMemcpyHostToDevice));
     if (beta != 0.0 && m > 0 && n > 0) CRP_CUDA_CHECK(cudaMemcpy2D(C_d, row_bytes, C_h, sizeof(double) * (size_t) ldC, row_bytes, (size_t) m, cudaMemcpyHostToDevice));
-    crp_cuda_spmm_exec(plan, n, 8, alpha, B_d, n, k, NULL, 0, beta, C_d, n, NULL);
+    crp_cuda_spmm_exec(plan, n, 8, alpha, B_d, n, NULL, 0, beta, C_d, n, NULL);
     CRP_CUDA_CHECK(cudaStreamSynchronize(0));
     if (m > 0 && n > 0) CRP_CUDA_CHECK(cudaMemcpy2D(C_h, sizeof(double) * (size_t) ldC, C_d, row_bytes, row_bytes, (size_t) m, cudaMemcpyDeviceToHost));
     CRP_CUDA_CHECK(cudaFree(B_d));

@@ -45,23 +45,30 @@ void  crp_nccl_shutdown(void);
 int  *crp_comm_ranks_in_parent(MPI_Comm sub, MPI_Comm parent);
 
 /* ---- device-side state of a row-parallel engine (rowpara_spmm.c) ---- */
+enum { CRP_EV_START = 0, CRP_EV_B_IN, CRP_EV_PACKED, CRP_EV_XCHG, CRP_EV_SPMM, CRP_EV_END, CRP_RP_NEV };
+
 struct crp_rp_dev
 {
     crp_spmm_plan *plan;        /* device CSR with "virtual" column ids (see rp_build_device_state) */
     int     nB;                 /* B rows owned by this rank                                         */
     int     n_send_rows;        /* rows packed per exec                                              */
     int     n_recv_rows;        /* remote rows received per exec                                     */
+    int     *send_rows;         /* nproc + 1, row offsets per destination in the send buffer         */
+    int     *recv_rows;         /* nproc + 1, row offsets per source in the receive buffer           */
     int     *d_sridxs;          /* device copy of rB_sridxs                                          */
     void    *d_sendbuf;  size_t sendbuf_bytes;
     void    *d_recvbuf;  size_t recvbuf_bytes;
     void    *d_Bwork;    size_t Bwork_bytes;   /* row-major device copy of B when the caller's is host / column-major */
     void    *d_Cwork;    size_t Cwork_bytes;
-    void    *d_Lwork;    size_t Lwork_bytes;   /* column-major staging for host + BC_layout = 1      */
+    void    *d_Lwork;    size_t Lwork_bytes;   /* column-major staging for BC_layout = 1             */
+    void    *h_sendbuf;  size_t h_sendbuf_bytes;   /* pinned, staged-MPI transport only              */
+    void    *h_recvbuf;  size_t h_recvbuf_bytes;
     void    *stream;            /* own non-blocking stream                                           */
-    void    *ev[5];             /* start, packed, exchanged, multiplied, end                         */
+    void    *ev[CRP_RP_NEV];
     int     pending;            /* events of the last exec not yet folded into the statistics        */
-    void    *pending_stream;
     double  pending_host_t0;
+    double  t_h2d, t_d2h;       /* staging of host B / C (seconds, device time)                      */
+    int     staged;             /* 1: exchange through pinned host memory + MPI (ranks share a GPU)  */
     crp_nccl_comm *nc;          /* NCCL communicator used for the B-row exchange                     */
     int     *peer_nc_rank;      /* nproc: rank of each member of rp->comm inside nc                  */
 };

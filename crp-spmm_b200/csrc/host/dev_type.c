@@ -11,10 +11,16 @@
 #include "dev_type.h"
 #include "crp_cuda.h"
 
+int crp_device_ready(void);     /* crp_common.c: binds this process to its GPU on first use */
+
 static int have_gpu(void)
 {
     static int cached = -1;
-    if (cached < 0) cached = (crp_cuda_device_count() > 0) ? 1 : 0;
+    if (cached < 0)
+    {
+        cached = (crp_cuda_device_count() > 0) ? 1 : 0;
+        if (cached) cached = crp_device_ready();
+    }
     return cached;
 }
 

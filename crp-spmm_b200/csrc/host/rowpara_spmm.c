@@ -1,0 +1,582 @@
+/*
+ * rowpara_spmm.c - 1-D row-parallel SpMM engine (include/rowpara_spmm.h).
+ *
+ * Host plan: a from-scratch restatement of what reference src/rowpara_spmm.c:46-184
+ * computes - the same index lists, counts and displacements, element for element
+ * (tests/ compare every public field against a build of the reference sources).
+ *
+ * Execution: nothing of the reference's exec survives.  The reference packs,
+ * exchanges, unpacks into a freshly malloc'd rB, copies its own rows into rB and
+ * builds an MKL handle on every call (src/rowpara_spmm.c:225-413).  Here
+ *   - the device CSR is created once at init, with "virtual" column ids: an id
+ *     below nB (the number of B rows this rank owns) addresses the caller's B
+ *     block directly, an id >= nB addresses row (id - nB) of the receive buffer.
+ *     The SpMM kernel therefore consumes its own rows and the received rows in
+ *     place: there is no rB, no unpack and no self copy;
+ *   - pack is one gather kernel over the flat (peer, row) list;
+ *   - the exchange is one grouped NCCL send/recv (byte counts = the reference's
+ *     rB_scnts / rB_rcnts), or, when several ranks share one GPU (more ranks
+ *     than devices - NCCL cannot do that), the same messages staged through
+ *     pinned host memory and MPI, like the reference's DEV_TYPE_CUDA staging
+ *     (src/mat_redist.c:362-378);
+ *   - all buffers persist between execs; phases are timed with CUDA events.
+ */
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mpi.h>
+
+#include "utils.h"
+#include "rowpara_spmm.h"
+#include "crp_ext.h"
+#include "crp_internal.h"
+
+/* ------------------------------------------------------------------ helpers */
+
+static void *xmalloc(size_t bytes)
+{
+    void *p = malloc(bytes > 0 ? bytes : 1);
+    ASSERT_PRINTF(p != NULL, "Failed to allocate %zu bytes of work memory for rp_spmm\n", bytes);
+    return p;
+}
+
+static void grow_dev(void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return;
+    crp_cuda_free_dev(*buf);
+    crp_cuda_malloc_dev(buf, need);
+    *cap = need;
+}
+
+static void grow_host(void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return;
+    crp_cuda_free_host(*buf);
+    crp_cuda_malloc_host(buf, need);
+    *cap = need;
+}
+
+/* ------------------------------------------------------------- host planning */
+
+/*
+ * Steps 1-5 of the reference init (src/rowpara_spmm.c:46-184).  Collective over comm
+ * (one MPI_Alltoall and one MPI_Alltoallv, as in the reference).
+ */
+static void rp_build_plan(
+    rp_spmm_p rp, const int A_nrow, const int *A_rowptr, const int *A_colidx, const double *A_val,
+    const int *B_row_displs, const int glb_n, MPI_Comm comm
+)
+{
+    const int nproc = rp->nproc, me = rp->my_rank;
+    const int reidx = rp->rB_reidx;
+    const int nnz_base = A_rowptr[0];
+    const int nnz = A_rowptr[A_nrow] - nnz_base;
+    const int glb_k = B_row_displs[nproc];
+
+    /* 1. column range of the local A, needed-row flags, compact copy of A */
+    int lo = INT_MAX, hi = 0;
+    for (int i = 0; i < nnz; i++)
+    {
+        const int c = A_colidx[i];
+        if (c < lo) lo = c;
+        if (c > hi) hi = c;
+    }
+    int *rowptr = (int *) xmalloc(sizeof(int) * ((size_t) A_nrow + 1));
+    int *colidx = (int *) xmalloc(sizeof(int) * (size_t) nnz);
+    double *val = (double *) xmalloc(sizeof(double) * (size_t) nnz);
+    for (int i = 0; i <= A_nrow; i++) rowptr[i] = A_rowptr[i] - nnz_base;
+    memcpy(val, A_val, sizeof(double) * (size_t) nnz);
+
+    unsigned char *needed = (unsigned char *) xmalloc((size_t) glb_k);
+    memset(needed, 0, (size_t) glb_k);
+    for (int i = 0; i < nnz; i++) needed[A_colidx[i]] = 1;
+
+    /* span == hi - lo + 1 also when nnz == 0 (the reference's INT_MAX arithmetic, kept for parity) */
+    int span = hi - lo + 1;
+    int rB_nrow = span;
+    int *pos_of = NULL;                 /* reidx: position in rB of global row lo + i */
+    if (reidx)
+    {
+        pos_of = (int *) xmalloc(sizeof(int) * (size_t) (span > 0 ? span : 1));
+        int cnt = 0;
+        for (int g = 0; g < glb_k; g++)
+            if (needed[g]) pos_of[g - lo] = cnt++;
+        rB_nrow = cnt;
+        for (int i = 0; i < nnz; i++) colidx[i] = pos_of[A_colidx[i] - lo];
+    } else {
+        for (int i = 0; i < nnz; i++) colidx[i] = A_colidx[i] - lo;
+    }
+    rp->A_rowptr = rowptr;
+    rp->A_colidx = colidx;
+    rp->A_val    = val;
+    rp->rB_nrow  = rB_nrow;
+
+    /* 2. rows taken from this rank's own B block */
+    const int my_lo = B_row_displs[me], my_hi = B_row_displs[me + 1];
+    int self_n = 0;
+    for (int g = my_lo; g < my_hi; g++) self_n += needed[g];
+    int *self_rows = (int *) xmalloc(sizeof(int) * (size_t) self_n);
+    self_n = 0;
+    for (int g = my_lo; g < my_hi; g++)
+        if (needed[g])
+        {
+            self_rows[self_n++] = g;
+            needed[g] = 0;          /* own rows are not requested from anybody */
+        }
+    rp->rB_self_nrow = self_n;
+    rp->rB_self_src_ridxs = self_rows;
+    rp->rB_self_src_offset = 0;
+    rp->rB_self_dst_offset = 0;
+    if (self_n > 0)
+    {
+        rp->rB_self_src_offset = self_rows[0] - my_lo;
+        rp->rB_self_dst_offset = reidx ? pos_of[self_rows[0] - lo] : self_rows[0] - lo;
+    }
+
+    /* 3. rows requested from every other owner, grouped by owner, ascending global id */
+    int *rcnts   = (int *) xmalloc(sizeof(int) * (size_t) nproc);
+    int *rdispls = (int *) xmalloc(sizeof(int) * ((size_t) nproc + 1));
+    int *rridxs  = (int *) xmalloc(sizeof(int) * (size_t) (rB_nrow > 0 ? rB_nrow : 1));
+    int nreq = 0;
+    rdispls[0] = 0;
+    for (int p = 0; p < nproc; p++)
+    {
+        int c = 0;
+        for (int g = B_row_displs[p]; g < B_row_displs[p + 1]; g++)
+            if (needed[g]) { rridxs[nreq++] = g; c++; }
+        rcnts[p] = c;
+        rdispls[p + 1] = rdispls[p] + c;
+    }
+    free(needed);
+    rp->rB_recv_size = (size_t) (rdispls[nproc] - rcnts[me]);
+
+    /* 4. tell every owner which of its rows this rank wants */
+    int *scnts   = (int *) xmalloc(sizeof(int) * (size_t) nproc);
+    int *sdispls = (int *) xmalloc(sizeof(int) * ((size_t) nproc + 1));
+    MPI_Alltoall(rcnts, 1, MPI_INT, scnts, 1, MPI_INT, comm);
+    sdispls[0] = 0;
+    for (int p = 0; p < nproc; p++) sdispls[p + 1] = sdispls[p] + scnts[p];
+    int *sridxs = (int *) xmalloc(sizeof(int) * (size_t) sdispls[nproc]);
+    MPI_Alltoallv(rridxs, rcnts, rdispls, MPI_INT, sridxs, scnts, sdispls, MPI_INT, comm);
+
+    /* 5. global ids -> positions (receive side: in rB; send side: in the own B block); counts in elements */
+    for (int i = 0; i < nreq; i++) rridxs[i] = reidx ? pos_of[rridxs[i] - lo] : rridxs[i] - lo;
+    for (int i = 0; i < sdispls[nproc]; i++) sridxs[i] -= my_lo;
+    for (int p = 0; p < nproc; p++)
+    {
+        rcnts[p] *= glb_n;  rdispls[p] *= glb_n;
+        scnts[p] *= glb_n;  sdispls[p] *= glb_n;
+    }
+    rdispls[nproc] *= glb_n;
+    sdispls[nproc] *= glb_n;
+    free(pos_of);
+
+    rp->rB_rcnts = rcnts;   rp->rB_rdispls = rdispls;   rp->rB_rridxs = rridxs;
+    rp->rB_scnts = scnts;   rp->rB_sdispls = sdispls;   rp->rB_sridxs = sridxs;
+}
+
+/* ------------------------------------------------------------- device state */
+
+/*
+ * Upload the local A with virtual column ids and the send list; size the
+ * persistent exchange buffers.  n_send_rows / n_recv_rows are recomputed from
+ * row counts kept in 64 bits (the public int counts are rows * glb_n and may
+ * wrap for very wide B, as they do in the reference).
+ */
+static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Comm nccl_parent)
+{
+    struct crp_rp_dev *d = (struct crp_rp_dev *) calloc(1, sizeof(struct crp_rp_dev));
+    ASSERT_PRINTF(d != NULL, "Failed to allocate device state for rp_spmm\n");
+    rp->dev = d;
+    const int nproc = rp->nproc, me = rp->my_rank, n = rp->glb_n;
+    const int nnz = rp->A_rowptr[rp->A_nrow];
+    d->nB = B_row_displs[me + 1] - B_row_displs[me];
+
+    /* row counts per peer (exact division: counts were rows * n) */
+    d->send_rows = (int *) xmalloc(sizeof(int) * ((size_t) nproc + 1));
+    d->recv_rows = (int *) xmalloc(sizeof(int) * ((size_t) nproc + 1));
+    d->send_rows[0] = d->recv_rows[0] = 0;
+    for (int p = 0; p < nproc; p++)
+    {
+        d->send_rows[p + 1] = d->send_rows[p] + (n > 0 ? rp->rB_scnts[p] / n : 0);
+        d->recv_rows[p + 1] = d->recv_rows[p] + (n > 0 ? rp->rB_rcnts[p] / n : 0);
+    }
+    d->n_send_rows = d->send_rows[nproc];
+    d->n_recv_rows = d->recv_rows[nproc];
+
+    /* rB position -> virtual id */
+    const int rB_nrow = rp->rB_nrow > 0 ? rp->rB_nrow : 0;
+    int *vid = (int *) xmalloc(sizeof(int) * (size_t) (rB_nrow > 0 ? rB_nrow : 1));
+    for (int i = 0; i < rB_nrow; i++) vid[i] = -1;
+    for (int i = 0; i < d->n_recv_rows; i++) vid[rp->rB_rridxs[i]] = d->nB + i;
+    for (int i = 0; i < rp->rB_self_nrow; i++)
+    {
+        const int step = rp->rB_self_src_ridxs[i] - rp->rB_self_src_ridxs[0];
+        const int dst = rp->rB_self_dst_offset + (rp->rB_reidx ? i : step);
+        vid[dst] = rp->rB_self_src_offset + step;
+    }
+    int *vcol = (int *) xmalloc(sizeof(int) * (size_t) (nnz > 0 ? nnz : 1));
+    for (int i = 0; i < nnz; i++)
+    {
+        vcol[i] = vid[rp->A_colidx[i]];
+        ASSERT_PRINTF(vcol[i] >= 0, "rp_spmm: column %d of the local A has no source row\n", rp->A_colidx[i]);
+    }
+    free(vid);
+    d->plan = crp_cuda_spmm_plan_create(rp->A_nrow, d->nB + d->n_recv_rows, d->nB, rp->A_rowptr, vcol, rp->A_val, n);
+    free(vcol);
+
+    if (d->n_send_rows > 0)
+    {
+        crp_cuda_malloc_dev((void **) &d->d_sridxs, sizeof(int) * (size_t) d->n_send_rows);
+        crp_cuda_memcpy_h2d(rp->rB_sridxs, d->d_sridxs, sizeof(int) * (size_t) d->n_send_rows);
+    }
+    d->stream = crp_cuda_stream_create();
+    for (int i = 0; i < CRP_RP_NEV; i++) d->ev[i] = crp_cuda_event_create();
+
+    /* transport: NCCL needs one device per rank */
+    int wsize = 1;
+    MPI_Comm_size(MPI_COMM_WORLD, &wsize);
+    int transport;
+    GET_ENV_INT_VAR(transport, "CRP_SPMM_TRANSPORT", "transport", -1, 0, 1, 0);   /* 0 NCCL, 1 staged MPI */
+    if (transport < 0) transport = (wsize > crp_cuda_device_count()) ? 1 : 0;
+    d->staged = transport;
+    d->nc = NULL;
+    d->peer_nc_rank = NULL;
+    if (nproc > 1 && !d->staged)
+    {
+        d->nc = crp_nccl_get(nccl_parent);
+        d->peer_nc_rank = crp_comm_ranks_in_parent(rp->comm, nccl_parent);
+    }
+}
+
+static void rp_free_device_state(rp_spmm_p rp)
+{
+    struct crp_rp_dev *d = (struct crp_rp_dev *) rp->dev;
+    if (d == NULL) return;
+    crp_cuda_stream_sync(d->stream);
+    crp_cuda_spmm_plan_destroy(d->plan);
+    crp_cuda_free_dev(d->d_sridxs);
+    crp_cuda_free_dev(d->d_sendbuf);
+    crp_cuda_free_dev(d->d_recvbuf);
+    crp_cuda_free_dev(d->d_Bwork);
+    crp_cuda_free_dev(d->d_Cwork);
+    crp_cuda_free_dev(d->d_Lwork);
+    crp_cuda_free_host(d->h_sendbuf);
+    crp_cuda_free_host(d->h_recvbuf);
+    for (int i = 0; i < CRP_RP_NEV; i++) crp_cuda_event_destroy(d->ev[i]);
+    crp_cuda_stream_destroy(d->stream);
+    free(d->send_rows);
+    free(d->recv_rows);
+    free(d->peer_nc_rank);
+    free(d);
+    rp->dev = NULL;
+}
+
+/* --------------------------------------------------------------- public API */
+
+void rp_spmm_init_on(
+    const int A_srow, const int A_nrow, const int *A_rowptr, const int *A_colidx,
+    const double *A_val, const int *B_row_displs, const int glb_n, MPI_Comm comm,
+    MPI_Comm nccl_parent, rp_spmm_p *rp_spmm
+)
+{
+    (void) A_srow;      /* unused in the reference as well */
+    rp_spmm_p rp = (rp_spmm_p) calloc(1, sizeof(rp_spmm_s));
+    ASSERT_PRINTF(rp != NULL, "Failed to allocate rp_spmm\n");
+    const double t0 = get_wtime_sec();
+
+    MPI_Comm_size(comm, &rp->nproc);
+    MPI_Comm_rank(comm, &rp->my_rank);
+    rp->A_nrow = A_nrow;
+    rp->glb_n  = glb_n;
+    rp->comm   = comm;
+    int wrank;
+    MPI_Comm_rank(MPI_COMM_WORLD, &wrank);
+    GET_ENV_INT_VAR(rp->rB_p2p,   "RP_SPMM_P2P",   "rB_p2p",   1, 0, 1, wrank == 0);
+    GET_ENV_INT_VAR(rp->rB_reidx, "RP_SPMM_REIDX", "rB_reidx", 1, 0, 1, wrank == 0);
+
+    rp_build_plan(rp, A_nrow, A_rowptr, A_colidx, A_val, B_row_displs, glb_n, comm);
+    if (crp_device_ready()) rp_build_device_state(rp, B_row_displs, nccl_parent);
+
+    rp->t_init = get_wtime_sec() - t0;
+    *rp_spmm = rp;
+}
+
+void rp_spmm_init(
+    const int A_srow, const int A_nrow, const int *A_rowptr, const int *A_colidx,
+    const double *A_val, const int *B_row_displs, const int glb_n, MPI_Comm comm,
+    rp_spmm_p *rp_spmm
+)
+{
+    rp_spmm_init_on(A_srow, A_nrow, A_rowptr, A_colidx, A_val, B_row_displs, glb_n, comm, comm, rp_spmm);
+}
+
+void rp_spmm_free(rp_spmm_p *rp_spmm)
+{
+    rp_spmm_p rp = *rp_spmm;
+    if (rp == NULL) return;
+    rp_free_device_state(rp);
+    free(rp->A_rowptr);
+    free(rp->A_colidx);
+    free(rp->A_val);
+    free(rp->rB_self_src_ridxs);
+    free(rp->rB_rcnts);
+    free(rp->rB_rdispls);
+    free(rp->rB_rridxs);
+    free(rp->rB_scnts);
+    free(rp->rB_sdispls);
+    free(rp->rB_sridxs);
+    free(rp);
+    *rp_spmm = NULL;
+}
+
+/* fold the events of the last exec into the statistics (after its stream work completed) */
+static void rp_collect(rp_spmm_p rp)
+{
+    struct crp_rp_dev *d = (struct crp_rp_dev *) rp->dev;
+    if (d == NULL || !d->pending) return;
+    crp_cuda_event_sync(d->ev[CRP_EV_END]);
+    rp->t_pack   += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_B_IN],   d->ev[CRP_EV_PACKED]);
+    rp->t_a2a    += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_PACKED], d->ev[CRP_EV_XCHG]);
+    rp->t_spmm   += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_XCHG],   d->ev[CRP_EV_SPMM]);
+    d->t_h2d     += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_START],  d->ev[CRP_EV_B_IN]);
+    d->t_d2h     += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_SPMM],   d->ev[CRP_EV_END]);
+    rp->t_exec   += get_wtime_sec() - d->pending_host_t0;
+    d->pending = 0;
+}
+
+/* the exchange of packed rows: device send buffer -> device receive buffer */
+static void rp_exchange(rp_spmm_p rp, struct crp_rp_dev *d, const size_t row_bytes, void *stream)
+{
+    const int nproc = rp->nproc, me = rp->my_rank;
+    if (nproc == 1 || (d->n_send_rows == 0 && d->n_recv_rows == 0)) return;
+    if (!d->staged)
+    {
+        crp_nccl_group_start();
+        for (int p = 0; p < nproc; p++)
+        {
+            if (p == me) continue;
+            const int ns = d->send_rows[p + 1] - d->send_rows[p];
+            const int nr = d->recv_rows[p + 1] - d->recv_rows[p];
+            if (ns > 0) crp_nccl_send(d->nc, (const char *) d->d_sendbuf + row_bytes * (size_t) d->send_rows[p], row_bytes * (size_t) ns, d->peer_nc_rank[p], stream);
+            if (nr > 0) crp_nccl_recv(d->nc, (char *) d->d_recvbuf + row_bytes * (size_t) d->recv_rows[p], row_bytes * (size_t) nr, d->peer_nc_rank[p], stream);
+        }
+        crp_nccl_group_end();
+        return;
+    }
+    /* several ranks on one GPU: stage through pinned host memory and MPI */
+    grow_host(&d->h_sendbuf, &d->h_sendbuf_bytes, row_bytes * (size_t) d->n_send_rows);
+    grow_host(&d->h_recvbuf, &d->h_recvbuf_bytes, row_bytes * (size_t) d->n_recv_rows);
+    if (d->n_send_rows > 0) crp_cuda_memcpy_async(d->d_sendbuf, d->h_sendbuf, row_bytes * (size_t) d->n_send_rows, stream);
+    crp_cuda_stream_sync(stream);
+    MPI_Request *reqs = (MPI_Request *) xmalloc(sizeof(MPI_Request) * 2 * (size_t) nproc);
+    int nreq = 0;
+    const size_t chunk = (size_t) 1 << 30;      /* MPI counts are ints */
+    for (int p = 0; p < nproc; p++)
+    {
+        if (p == me) continue;
+        const size_t nr = row_bytes * (size_t) (d->recv_rows[p + 1] - d->recv_rows[p]);
+        ASSERT_PRINTF(nr < chunk * 2, "rp_spmm staged exchange: message of %zu bytes is too large\n", nr);
+        if (nr > 0) MPI_Irecv((char *) d->h_recvbuf + row_bytes * (size_t) d->recv_rows[p], (int) nr, MPI_BYTE, p, p, rp->comm, &reqs[nreq++]);
+    }
+    for (int p = 0; p < nproc; p++)
+    {
+        if (p == me) continue;
+        const size_t ns = row_bytes * (size_t) (d->send_rows[p + 1] - d->send_rows[p]);
+        ASSERT_PRINTF(ns < chunk * 2, "rp_spmm staged exchange: message of %zu bytes is too large\n", ns);
+        if (ns > 0) MPI_Isend((const char *) d->h_sendbuf + row_bytes * (size_t) d->send_rows[p], (int) ns, MPI_BYTE, p, me, rp->comm, &reqs[nreq++]);
+    }
+    MPI_Waitall(nreq, reqs, MPI_STATUSES_IGNORE);
+    free(reqs);
+    if (d->n_recv_rows > 0) crp_cuda_memcpy_async(d->h_recvbuf, d->d_recvbuf, row_bytes * (size_t) d->n_recv_rows, stream);
+}
+
+void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const int ldB, void *C, const int ldC, const int elem_size)
+{
+    if (rp == NULL) return;
+    struct crp_rp_dev *d = (struct crp_rp_dev *) rp->dev;
+    if (d == NULL)
+    {
+        fprintf(stderr, "[FATAL] rp_spmm_exec: this engine has no device state (plan-only mode or no GPU); there is no CPU path\n");
+        fflush(stderr);
+        abort();
+    }
+    rp_collect(rp);
+    const double host_t0 = get_wtime_sec();
+    const int n = rp->glb_n, m = rp->A_nrow, nB = d->nB;
+    const size_t es = (size_t) elem_size;
+    const size_t row_bytes = es * (size_t) n;
+    void *stream = crp_opt_stream() ? crp_opt_stream() : d->stream;
+    const int B_on_dev = (nB > 0 && n > 0) ? crp_cuda_ptr_is_device(B) : 1;
+    const int C_on_dev = (m > 0 && n > 0) ? crp_cuda_ptr_is_device(C) : 1;
+
+    crp_cuda_event_record(d->ev[CRP_EV_START], stream);
+
+    /* ---- B as a row-major device matrix Bd (leading dimension ldBd) ---- */
+    const void *Bd = B;
+    size_t ldBd = (size_t) ldB;
+    if (nB > 0 && n > 0)
+    {
+        if (BC_layout == 0)
+        {
+            if (!B_on_dev)
+            {
+                crp_pin_host_range(B, es * ((size_t) (nB - 1) * (size_t) ldB + (size_t) n));
+                grow_dev(&d->d_Bwork, &d->Bwork_bytes, row_bytes * (size_t) nB);
+                crp_cuda_memcpy2d_async(B, es * (size_t) ldB, d->d_Bwork, row_bytes, row_bytes, (size_t) nB, stream);
+                Bd = d->d_Bwork;
+                ldBd = (size_t) n;
+            }
+        } else {
+            /* column-major nB x n with leading dimension ldB == row-major n x nB */
+            const void *Bcm = B;
+            size_t ldcm = (size_t) ldB;
+            if (!B_on_dev)
+            {
+                crp_pin_host_range(B, es * ((size_t) (n - 1) * (size_t) ldB + (size_t) nB));
+                grow_dev(&d->d_Lwork, &d->Lwork_bytes, es * (size_t) nB * (size_t) n);
+                crp_cuda_memcpy2d_async(B, es * (size_t) ldB, d->d_Lwork, es * (size_t) nB, es * (size_t) nB, (size_t) n, stream);
+                Bcm = d->d_Lwork;
+                ldcm = (size_t) nB;
+            }
+            grow_dev(&d->d_Bwork, &d->Bwork_bytes, row_bytes * (size_t) nB);
+            crp_cuda_transpose(es, n, nB, Bcm, (int) ldcm, d->d_Bwork, n, stream);
+            Bd = d->d_Bwork;
+            ldBd = (size_t) n;
+        }
+    }
+    crp_cuda_event_record(d->ev[CRP_EV_B_IN], stream);
+
+    /* ---- pack the rows other ranks need ---- */
+    if (d->n_send_rows > 0 && n > 0)
+    {
+        grow_dev(&d->d_sendbuf, &d->sendbuf_bytes, row_bytes * (size_t) d->n_send_rows);
+        crp_cuda_gather_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, d->d_sendbuf, n, stream);
+    }
+    if (d->n_recv_rows > 0 && n > 0) grow_dev(&d->d_recvbuf, &d->recvbuf_bytes, row_bytes * (size_t) d->n_recv_rows);
+    crp_cuda_event_record(d->ev[CRP_EV_PACKED], stream);
+
+    /* ---- exchange ---- */
+    if (n > 0) rp_exchange(rp, d, row_bytes, stream);
+    crp_cuda_event_record(d->ev[CRP_EV_XCHG], stream);
+
+    /* ---- local product, reading own rows from Bd and remote rows from the receive buffer ---- */
+    void *Cd = C;
+    size_t ldCd = (size_t) ldC;
+    const int C_direct = (BC_layout == 0) && C_on_dev;
+    if (m > 0 && n > 0)
+    {
+        if (!C_direct)
+        {
+            grow_dev(&d->d_Cwork, &d->Cwork_bytes, row_bytes * (size_t) m);
+            Cd = d->d_Cwork;
+            ldCd = (size_t) n;
+        }
+        crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
+    }
+    crp_cuda_event_record(d->ev[CRP_EV_SPMM], stream);
+
+    /* ---- C back to where the caller wants it ---- */
+    if (m > 0 && n > 0 && !C_direct)
+    {
+        if (BC_layout == 0)
+        {
+            crp_pin_host_range(C, es * ((size_t) (m - 1) * (size_t) ldC + (size_t) n));
+            crp_cuda_memcpy2d_async(Cd, row_bytes, C, es * (size_t) ldC, row_bytes, (size_t) m, stream);
+        } else if (C_on_dev) {
+            crp_cuda_transpose(es, m, n, Cd, n, C, ldC, stream);
+        } else {
+            crp_pin_host_range(C, es * ((size_t) (n - 1) * (size_t) ldC + (size_t) m));
+            grow_dev(&d->d_Lwork, &d->Lwork_bytes, es * (size_t) m * (size_t) n);
+            crp_cuda_transpose(es, m, n, Cd, n, d->d_Lwork, m, stream);
+            crp_cuda_memcpy2d_async(d->d_Lwork, es * (size_t) m, C, es * (size_t) ldC, es * (size_t) m, (size_t) n, stream);
+        }
+    }
+    crp_cuda_event_record(d->ev[CRP_EV_END], stream);
+
+    d->pending = 1;
+    d->pending_host_t0 = host_t0;
+    rp->n_exec++;
+    if (crp_opt_blocking() || !C_on_dev || !B_on_dev) rp_collect(rp);
+}
+
+void rp_spmm_exec(rp_spmm_p rp_spmm, const int BC_layout, const double *B, const int ldB, double *C, const int ldC)
+{
+    rp_spmm_exec_any(rp_spmm, BC_layout, B, ldB, C, ldC, 8);
+}
+
+void rp_spmm_exec_f32(rp_spmm_p rp_spmm, const int BC_layout, const float *B, const int ldB, float *C, const int ldC)
+{
+    rp_spmm_exec_any(rp_spmm, BC_layout, B, ldB, C, ldC, 4);
+}
+
+const char *rp_spmm_kernel_name(rp_spmm_p rp)
+{
+    if (rp == NULL || rp->dev == NULL) return "none";
+    return crp_cuda_spmm_last_kernel(((struct crp_rp_dev *) rp->dev)->plan);
+}
+
+void rp_spmm_set_kernel(rp_spmm_p rp, const char *name)
+{
+    if (rp == NULL || rp->dev == NULL) return;
+    crp_cuda_spmm_set_variant(((struct crp_rp_dev *) rp->dev)->plan, name);
+}
+
+int rp_spmm_is_plan_only(rp_spmm_p rp) { return (rp != NULL && rp->dev == NULL) ? 1 : 0; }
+
+void rp_spmm_device_times(rp_spmm_p rp, double *t_h2d, double *t_d2h)
+{
+    *t_h2d = *t_d2h = 0.0;
+    if (rp == NULL || rp->dev == NULL) return;
+    rp_collect(rp);
+    *t_h2d = ((struct crp_rp_dev *) rp->dev)->t_h2d;
+    *t_d2h = ((struct crp_rp_dev *) rp->dev)->t_d2h;
+}
+
+/* Same table, same row labels as the reference (src/rowpara_spmm.c:425-464). */
+void rp_spmm_print_stat(rp_spmm_p rp)
+{
+    if (rp == NULL) return;
+    rp_collect(rp);
+    const int n_exec = rp->n_exec;
+    if (n_exec == 0) return;
+    unsigned long long recv_rows = (unsigned long long) rp->rB_recv_size, recv_max = 0, recv_sum = 0;
+    double raw[6] = { rp->t_init, rp->t_pack, rp->t_a2a, rp->t_unpack, rp->t_spmm, rp->t_exec };
+    double tmax[6], tavg[6];
+    MPI_Reduce(&recv_rows, &recv_max, 1, MPI_UNSIGNED_LONG_LONG, MPI_MAX, 0, rp->comm);
+    MPI_Reduce(&recv_rows, &recv_sum, 1, MPI_UNSIGNED_LONG_LONG, MPI_SUM, 0, rp->comm);
+    MPI_Reduce(raw, tmax, 6, MPI_DOUBLE, MPI_MAX, 0, rp->comm);
+    MPI_Reduce(raw, tavg, 6, MPI_DOUBLE, MPI_SUM, 0, rp->comm);
+    if (rp->my_rank != 0) return;
+    for (int i = 1; i < 6; i++)
+    {
+        tmax[i] /= n_exec;
+        tavg[i] /= (double) n_exec * rp->nproc;
+    }
+    printf("rp_spmm_init() time = %.2f s\n", tmax[0]);
+    printf("Total / rank-max SpMM comm size = %zu, %zu\n", (size_t) (recv_sum * (unsigned long long) rp->glb_n), (size_t) (recv_max * (unsigned long long) rp->glb_n));
+    printf("-------------------- Runtime (s) --------------------\n");
+    printf("                                     avg         max\n");
+    printf("Pack B matrix for redistribution  %6.3f      %6.3f\n", tavg[1], tmax[1]);
+    printf("Redistribute B matrix             %6.3f      %6.3f\n", tavg[2], tmax[2]);
+    printf("Unpack received B matrix data     %6.3f      %6.3f\n", tavg[3], tmax[3]);
+    printf("Local SpMM                        %6.3f      %6.3f\n", tavg[4], tmax[4]);
+    printf("Total rp_spmm_exec()              %6.3f      %6.3f\n", tavg[5], tmax[5]);
+    printf("\n");
+    fflush(stdout);
+}
+
+void rp_spmm_clear_stat(rp_spmm_p rp)
+{
+    if (rp == NULL) return;
+    rp_collect(rp);
+    rp->n_exec   = 0;
+    rp->t_pack   = 0.0;
+    rp->t_a2a    = 0.0;
+    rp->t_unpack = 0.0;
+    rp->t_spmm   = 0.0;
+    rp->t_exec   = 0.0;
+    if (rp->dev) ((struct crp_rp_dev *) rp->dev)->t_h2d = ((struct crp_rp_dev *) rp->dev)->t_d2h = 0.0;
+}

@@ -222,14 +222,23 @@ def write_csr_bin(path, m, k, rowptr, colidx, val):
         np.ascontiguousarray(val, dtype=np.float64).tofile(f)
 
 
-def read_csr_bin(path):
+def read_csr_bin(path, mmap=False):
+    """(m, k, rowptr, colidx, val); with mmap=True the three arrays are read-only maps of the file."""
     with open(path, "rb") as f:
         assert f.read(8) == MAGIC
-        m, k, nnz = np.fromfile(f, dtype=np.int64, count=3)
+        m, k, nnz = (int(x) for x in np.fromfile(f, dtype=np.int64, count=3))
+        if mmap:
+            off = 32
+            rowptr = np.memmap(path, dtype=np.int32, mode="r", offset=off, shape=(m + 1,))
+            off += 4 * (m + 1)
+            colidx = np.memmap(path, dtype=np.int32, mode="r", offset=off, shape=(nnz,)) if nnz else np.zeros(0, np.int32)
+            off += 4 * nnz
+            val = np.memmap(path, dtype=np.float64, mode="r", offset=off, shape=(nnz,)) if nnz else np.zeros(0, np.float64)
+            return m, k, rowptr, colidx, val
         rowptr = np.fromfile(f, dtype=np.int32, count=m + 1)
         colidx = np.fromfile(f, dtype=np.int32, count=nnz)
         val = np.fromfile(f, dtype=np.float64, count=nnz)
-    return int(m), int(k), rowptr, colidx, val
+    return m, k, rowptr, colidx, val
 
 
 def write_mtx(path, m, k, rowptr, colidx, val):

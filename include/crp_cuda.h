@@ -95,19 +95,19 @@ void crp_cuda_transpose(size_t dt_size, const int nrow, const int ncol, const vo
 typedef struct crp_spmm_plan crp_spmm_plan;
 
 /* Upload a 0-based CSR matrix (host arrays; m rows, column indices < k) and
- * prepare whatever auxiliary structures the kernels want.  n_hint is the
- * expected dense width (0 = unknown). */
-crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint);
+ * prepare whatever auxiliary structures the kernels want.
+ * The dense operand X of the product is given in two pieces at exec time:
+ * rows [0, x0_rows) live in X0, rows [x0_rows, k) in X1 (x0_rows >= k: one piece).
+ * n_hint is the expected dense width (0 = unknown). */
+crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int x0_rows, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint);
 void crp_cuda_spmm_plan_destroy(crp_spmm_plan *plan);
 
 /* C (m x n, row-major, ldc) := alpha * A * X + beta * C   (beta == 0: C is not read).
- * X is the row-major matrix whose rows [0, x0_rows) live in X0 (leading dimension ldx0)
- * and rows >= x0_rows in X1 (leading dimension ldx1, row r at X1 + (r - x0_rows) * ldx1);
- * pass x0_rows >= k and X1 = NULL for a single piece.
+ * X row r is X0 + r * ldx0 for r < x0_rows, else X1 + (r - x0_rows) * ldx1 (both row-major).
  * elem_size 8: X, C are fp64.  elem_size 4: X, C are fp32 and A's values are used as fp32. */
 void crp_cuda_spmm_exec(
     crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
-    const void *X0, const int ldx0, const int x0_rows, const void *X1, const int ldx1,
+    const void *X0, const int ldx0, const void *X1, const int ldx1,
     const double beta, void *C, const int ldc, void *stream
 );
 /* name of the kernel variant the last crp_cuda_spmm_exec on this plan launched (static string) */

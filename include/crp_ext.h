@@ -34,6 +34,9 @@ const char *rp_spmm_kernel_name(rp_spmm_p rp_spmm);
 /* Force a variant ("auto", "rowsplit", "rowblock", "mergepath") for experiments. */
 void rp_spmm_set_kernel(rp_spmm_p rp_spmm, const char *name);
 
+/* Device time (seconds since the last clear_stat) spent staging a host B in / a host C out. */
+void rp_spmm_device_times(rp_spmm_p rp_spmm, double *t_h2d, double *t_d2h);
+
 /* 1 if the engine was created in plan-only mode (CRP_SPMM_PLAN_ONLY=1, no device state). */
 int rp_spmm_is_plan_only(rp_spmm_p rp_spmm);
 
