@@ -14,8 +14,8 @@ BINDIR  := $(PKG)/bin
 OBJDIR  := $(ROOT)/build/obj
 MINIMPI := $(PKG)/minimpi
 
-CC      ?= gcc
-NVCC    ?= nvcc
+CC      := $(or $(CRP_CC),gcc)
+NVCC    := $(or $(CRP_NVCC),nvcc)
 CFLAGS  := -O2 -g -std=gnu11 -fPIC -fopenmp -Wall -Wno-unused-function -I$(ROOT)/include -I$(MINIMPI) -I$(SRC)/host -I/usr/local/cuda/include
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function \
            -I$(ROOT)/include -I$(SRC)/cuda $(CRP_NVCC_EXTRA)

@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py - SpMM GFLOP/s (2 nnz n / s) of the CRP-SpMM hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pwtk|er|rmat|stencil]
+    N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step is one para2d_spmm_exec (replicate B -> local SpMM) of the whole job on the
+BASELINE.json workload: the pwtk-shaped matrix (217,918^2, ~53 nnz/row, bandwidth 189,331),
+n = 256, fp64, cut into the cost model's pm x pn grid over the N ranks (strong scaling:
+total work is fixed).  The bundled mini-MPI carries the control plane (it bootstraps from
+torchrun's RANK / WORLD_SIZE / MASTER_PORT), NCCL the data plane.
+
+`value`       B and C resident in HBM, per-step CUDA-event time on the launching stream,
+              L2 flushed (256 MiB memset) between steps, max over ranks.
+`e2e`         the same call with pinned HOST B and C (H2D of B and D2H of C inside the timed region).
+`roofline`    local-SpMM kernel: algorithmic bytes / CUDA-event kernel time vs MEASURED_PEAKS.json.
+`cpu_baseline` the reference's own sources (oracle/_ref: reference C + mini-MPI + OpenMP stand-in for MKL)
+              on this box's host cores, 4 ranks as in BASELINE.json configs[0]; N = 1, rank 0 only.
+--impl reference prints the reference arm (CPU) for the same config and metric.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "crp-spmm_b200")
+sys.path.insert(0, PKG)
+
+import numpy as np  # noqa: E402
+
+METRIC = "SpMM GFLOP/s (2*nnz*n/s)"
+
+WORKLOADS = {
+    # name: (generator, kwargs, n, dtype, driver mode, description)
+    "pwtk":    ("pwtk_like", {}, 256, "f64", "2d", "pwtk-shaped banded SPD 217918x217918, ~53 nnz/row, bandwidth 189331 (BASELINE configs[1])"),
+    "er":      ("erdos_renyi", {"scale": 22, "nnz_per_row": 16}, 64, "f64", "rp", "Erdos-Renyi 4M x 4M, 16 nnz/row (BASELINE configs[2])"),
+    "rmat":    ("rmat", {"scale": 22, "edge_factor": 32}, 128, "f64", "2d", "RMAT scale 22, edge factor 32 (BASELINE configs[3])"),
+    "stencil": ("stencil27", {"n": 128}, 1024, "f32", "2d", "27-point stencil 128^3, n=1024 fp32 (BASELINE configs[4])"),
+    "pwtk_small": ("pwtk_like", {"m": 20000, "target_nnz": 1060000, "bandwidth": 17000, "grid_w": 32}, 64, "f64", "2d", "small pwtk-shaped test matrix"),
+}
+
+
+def matrix_path(workload):
+    """Binary CSR of the workload, generated once per box (rank 0) into the temp dir."""
+    gname, kw, *_ = WORKLOADS[workload]
+    path = os.path.join(tempfile.gettempdir(), f"crp_bench_{workload}.bin")
+    if not os.path.exists(path):
+        from pycrp import gen
+        m, k, rp, ci, v = getattr(gen, gname)(**kw)
+        tmp = path + f".{os.getpid()}"
+        gen.write_csr_bin(tmp, m, k, rp, ci, v)
+        os.replace(tmp, path)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference_cpu(csr, n, mode, steps, nranks=4):
+    """The reference sources under oracle/_ref on the host cores: returns (gflops, seconds per exec, cores, sample)."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    exe, run = os.path.join(ref, "ref_dump.exe"), os.path.join(ref, "minimpirun")
+    if not (os.path.exists(exe) and os.path.exists(run)):
+        return None
+    cores = os.cpu_count() or 1
+    nranks = min(nranks, cores)
+    thr = max(1, cores // nranks)
+    env = dict(os.environ, OMP_NUM_THREADS=str(thr), OMP_PLACES="cores", OMP_PROC_BIND="close")
+    for k_ in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT", "MASTER_ADDR", "TORCHELASTIC_RUN_ID", "MINIMPI_DIR", "MINIMPI_RANK", "MINIMPI_SIZE"):
+        env.pop(k_, None)
+    out = subprocess.run([run, "-np", str(nranks), exe, csr, str(n), str(steps), mode, "-"], capture_output=True, text=True, env=env, timeout=1500)
+    if out.returncode != 0:
+        raise RuntimeError("reference CPU run failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+    mobj = re.search(r"REFDUMP exec_s min ([\d.eE+-]+) avg ([\d.eE+-]+) max ([\d.eE+-]+) local_spmm_max_s ([\d.eE+-]+)", out.stdout)
+    g = re.search(r"REFDUMP grid (\d+) (\d+) .* nnz (\d+)", out.stdout)
+    avg = float(mobj.group(2))
+    nnz = int(g.group(3))
+    return {"gflops": 2.0 * nnz * n / avg / 1e9, "sec": avg, "cores": nranks * thr, "ranks": nranks, "threads": thr,
+            "grid": f"{g.group(1)}x{g.group(2)}", "local_spmm_s": float(mobj.group(4)), "steps": steps}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pwtk", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the dense width")
+    ap.add_argument("--kernel", default="auto", help="force a local-SpMM kernel variant")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    gname, gkw, n, dtype_s, mode, desc = WORKLOADS[a.workload]
+    n = a.n or n
+    rank_env = int(os.environ.get("RANK", "0"))
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank_env != 0:
+            return 0
+        csr = matrix_path(a.workload)
+        steps = max(1, min(a.steps, 5))
+        r = run_reference_cpu(csr, n, mode, steps, nranks=4)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) is missing"}))
+            return 0
+        sample = f"whole workload, {r['steps']} timed execs after 1 warm-up, {r['ranks']} ranks x {r['threads']} OpenMP threads, grid {r['grid']}"
+        line = {"impl": "reference", "metric": METRIC, "value": r["gflops"], "unit": "GFLOP/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": 1,
+                "ms_per_step": 1e3 * r["sec"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_s, "data": "synthetic",
+                "config": {"workload": desc, "n": n, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow"},
+                "cpu_baseline": {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["cores"], "kind": "reference", "sample": sample,
+                                 "note": "reference C sources + mini-MPI; MKL unavailable offline -> OpenMP CSR stand-in"},
+                "e2e": {"value": r["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (B200)
+    from pycrp import capi
+    from pycrp.flow import Problem
+    L = capi.load()
+    if L.crp_cuda_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device visible; the CRP-SpMM engine has no CPU path")
+    rank, nproc = capi.mpi_init()
+    assert nproc == world_env, (nproc, world_env)
+    if rank == 0:
+        csr = matrix_path(a.workload)
+    capi.mpi_barrier()
+    csr = matrix_path(a.workload)
+    dtype = np.float32 if dtype_s == "f32" else np.float64
+    pb = Problem(csr, n, mode, 0, dtype, rank, nproc).init()
+    if a.kernel != "auto":
+        L.rp_spmm_set_kernel(pb.rp, a.kernel.encode())
+    nnz, flops_total = pb.nnz, 2.0 * pb.nnz * n
+
+    stream = L.crp_cuda_stream_create()
+    L.crp_set_stream(stream)
+    B = pb.make_B()
+    C_ = pb.empty_C()
+    dB, dC = capi.DevBuf.from_numpy(B), capi.DevBuf(C_.nbytes)
+    flush_bytes = 256 << 20
+    dF = capi.DevBuf(flush_bytes)
+    ev = [(L.crp_cuda_event_create(), L.crp_cuda_event_create()) for _ in range(a.steps)]
+
+    def device_steps(count, timed):
+        L.crp_set_blocking(0)
+        for it in range(count):
+            L.crp_cuda_memset_async(dF.p, it & 0xff, flush_bytes, stream)          # L2 flush, outside the event pair
+            if timed:
+                L.crp_cuda_event_record(ev[it][0], stream)
+            pb.exec_ptr(dB.p, dC.p)
+            if timed:
+                L.crp_cuda_event_record(ev[it][1], stream)
+        L.crp_cuda_stream_sync(stream)
+        L.crp_set_blocking(1)
+
+    device_steps(a.warmup, False)
+    pb.clear_stat()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    capi.mpi_barrier()
+    L.crp_cuda_device_sync()
+    launches0 = L.crp_kernel_launch_count()
+    t0 = time.time()
+    device_steps(a.steps, True)
+    L.crp_cuda_device_sync()
+    capi.mpi_barrier()
+    t1 = time.time()
+    launches = L.crp_kernel_launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    my_ms = sum(L.crp_cuda_event_elapsed_ms(s, e) for s, e in ev) / a.steps
+    ms_per_step = capi.mpi_allreduce_max(my_ms)
+    value = flops_total / (ms_per_step * 1e-3) / 1e9
+
+    # roofline of the local-SpMM kernel, from the engine's own CUDA events around it (same timed region)
+    r = pb.rp.contents
+    t_spmm = r.t_spmm / max(r.n_exec, 1)
+    t_pack, t_a2a = r.t_pack / max(r.n_exec, 1), r.t_a2a / max(r.n_exec, 1)
+    bytes_loc, flops_loc = pb.algorithmic_bytes()
+    kern = L.rp_spmm_kernel_name(pb.rp).decode()
+    t_spmm_max = capi.mpi_allreduce_max(t_spmm)
+    bytes_sum = capi.mpi_allreduce_sum(float(bytes_loc))
+    recv_bytes = float(r.rB_recv_size) * r.glb_n * dtype().itemsize
+    recv_max = capi.mpi_allreduce_max(recv_bytes)
+    t_a2a_max = capi.mpi_allreduce_max(t_a2a)
+    peak, peak_src = measured_peak_hbm()
+    ach = bytes_loc / t_spmm / 1e9 if t_spmm > 0 else 0.0
+    ach_job = bytes_sum / t_spmm_max / 1e9 / nproc if t_spmm_max > 0 else 0.0
+
+    # checksum of the device-resident result (parity of the timed run itself, see also tests/)
+    C_dev = dC.to_numpy(C_.shape, C_.dtype)
+    csum = capi.mpi_allreduce_sum(float(np.sum(C_dev.astype(np.float64))))
+
+    # ---- e2e: host B / C through the same public call ----
+    e2e = None
+    if not a.no_e2e:
+        hB, hC = capi.C.c_void_p(), capi.C.c_void_p()
+        L.crp_cuda_malloc_host(capi.C.byref(hB), max(B.nbytes, 1))
+        L.crp_cuda_malloc_host(capi.C.byref(hC), max(C_.nbytes, 1))
+        capi.C.memmove(hB, capi.ptr(B), B.nbytes)
+        e2e_steps = max(3, min(a.steps, 10))
+        for _ in range(2):
+            pb.exec_ptr(hB, hC)
+        capi.mpi_barrier()
+        es, ee = L.crp_cuda_event_create(), L.crp_cuda_event_create()
+        L.crp_cuda_event_record(es, stream)
+        for _ in range(e2e_steps):
+            pb.exec_ptr(hB, hC)                      # blocking: returns when C is back in host memory
+        L.crp_cuda_event_record(ee, stream)
+        L.crp_cuda_event_sync(ee)
+        capi.mpi_barrier()
+        e2e_ms = capi.mpi_allreduce_max(L.crp_cuda_event_elapsed_ms(es, ee) / e2e_steps)
+        hC_np = np.ctypeslib.as_array(capi.C.cast(hC, capi.C.POINTER(capi.C.c_double if dtype == np.float64 else capi.C.c_float)), shape=C_.shape)
+        e2e_ok = bool(np.array_equal(hC_np, C_dev))
+        h2d = capi.mpi_allreduce_sum(float(B.nbytes))
+        d2h = capi.mpi_allreduce_sum(float(C_.nbytes))
+        e2e = {"value": flops_total / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_result": e2e_ok}
+        L.crp_cuda_free_host(hB)
+        L.crp_cuda_free_host(hC)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and nproc == 1 and not a.no_cpu_baseline:
+        try:
+            rr = run_reference_cpu(csr, n, mode, 3, nranks=4)
+            if rr is not None:
+                cpu = {"value": rr["gflops"], "unit": "GFLOP/s", "cores": rr["cores"], "kind": "reference",
+                       "sample": f"whole workload, 3 timed execs after 1 warm-up, {rr['ranks']} ranks x {rr['threads']} OpenMP threads, grid {rr['grid']}, "
+                                 f"{1e3 * rr['sec']:.1f} ms/exec (local SpMM {1e3 * rr['local_spmm_s']:.1f} ms)",
+                       "note": "reference C sources + mini-MPI; MKL unavailable offline -> OpenMP CSR stand-in"}
+        except Exception as exc:      # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {exc}"[:300]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": nproc, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_s, "data": "synthetic",
+            "config": {"workload": desc, "n": n, "nnz": nnz, "grid": f"{pb.pm}x{pb.pn}", "comm_cost": pb.comm_cost,
+                       "l2": "256 MiB memset between timed steps (outside the event pairs); B + C + A = %.0f MB per job" % (bytes_sum / 1e6),
+                       "kernel": kern, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow", "checksum": csum},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": ach if nproc == 1 else ach_job, "peak": peak, "unit": "GB/s",
+                         "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": None, "peak_source": peak_src, "kernel": kern,
+                         "algorithmic_bytes_per_launch": bytes_loc if nproc == 1 else bytes_sum / nproc, "kernel_ms": 1e3 * (t_spmm if nproc == 1 else t_spmm_max),
+                         "kernel_gflops": flops_loc / t_spmm / 1e9 if t_spmm > 0 else 0.0},
+            "phases_ms": {"pack": 1e3 * t_pack, "exchange": 1e3 * t_a2a_max, "local_spmm": 1e3 * t_spmm_max},
+            "nvlink": None if nproc == 1 or t_a2a_max <= 0 else {"recv_bytes_max": recv_max, "achieved_gbs": recv_max / t_a2a_max / 1e9, "peak_gbs": 770.0,
+                                                                   "frac": recv_max / t_a2a_max / 1e9 / 770.0, "peak_source": "measured peer copy, B200_PROFILING.md"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+        sys.stdout.flush()
+    pb.free()
+    capi.mpi_barrier()
+    capi.mpi_finalize()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -102,6 +102,11 @@ extern "C" void crp_cuda_memset_dev(void *dptr, const int value, const size_t by
     if (bytes) CRP_CUDA_CHECK(cudaMemset(dptr, value, bytes));
 }
 
+extern "C" void crp_cuda_memset_async(void *dptr, const int value, const size_t bytes, void *stream)
+{
+    if (bytes) CRP_CUDA_CHECK(cudaMemsetAsync(dptr, value, bytes, as_stream(stream)));
+}
+
 extern "C" void crp_cuda_memcpy_h2d(const void *hptr, void *dptr, const size_t bytes)
 {
     if (bytes) CRP_CUDA_CHECK(cudaMemcpy(dptr, hptr, bytes, cudaMemcpyHostToDevice));

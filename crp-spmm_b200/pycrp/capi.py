@@ -153,6 +153,7 @@ def load():
     L.crp_cuda_free_dev.argtypes = [vp]
     L.crp_cuda_free_host.argtypes = [vp]
     L.crp_cuda_memset_dev.argtypes = [vp, i, sz]
+    L.crp_cuda_memset_async.argtypes = [vp, i, sz, vp]
     L.crp_cuda_memcpy_h2d.argtypes = [vp, vp, sz]
     L.crp_cuda_memcpy_d2h.argtypes = [vp, vp, sz]
     L.crp_cuda_memcpy_d2d.argtypes = [vp, vp, sz]

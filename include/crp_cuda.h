@@ -44,6 +44,7 @@ void crp_cuda_malloc_host(void **hptr_, const size_t bytes);   /* pinned */
 void crp_cuda_free_dev(void *dptr);
 void crp_cuda_free_host(void *hptr);
 void crp_cuda_memset_dev(void *dptr, const int value, const size_t bytes);
+void crp_cuda_memset_async(void *dptr, const int value, const size_t bytes, void *stream);
 void crp_cuda_memcpy_h2d(const void *hptr, void *dptr, const size_t bytes);
 void crp_cuda_memcpy_d2h(const void *dptr, void *hptr, const size_t bytes);
 void crp_cuda_memcpy_d2d(const void *dptr_src, void *dptr_dst, const size_t bytes);
