@@ -30,7 +30,23 @@ void crp_count_launch();
 static inline cudaStream_t as_stream(void *s) { return (cudaStream_t) s; }
 
 // ---- SpMM plan: device CSR + auxiliary structures of the kernel variants ----
-enum { CRP_VARIANT_AUTO = 0, CRP_VARIANT_ROWSPLIT = 1, CRP_VARIANT_ROWBLOCK = 2, CRP_VARIANT_MERGEPATH = 3 };
+enum { CRP_VARIANT_AUTO = 0, CRP_VARIANT_ROWSPLIT = 1, CRP_VARIANT_ROWGROUP = 2, CRP_VARIANT_MERGEPATH = 3 };
+
+// row-group (register-blocked) decomposition, see spmm_rowgroup.cu
+struct crp_rowgroup
+{
+    int       R;                // rows per group (0: not built / not worthwhile)
+    int       ngroups;          // groups stored as R x 1 column blocks
+    long long nblk;             // blocks in total
+    int       nrest;            // rows left to the row-split kernel
+    long long rest_nnz;
+    int       *d_grow;          // ngroups: first row of each group
+    int       *d_gptr;          // ngroups + 1: block range of each group
+    int       *d_bcol;          // nblk: column of each block
+    double    *d_bval;          // nblk * R: values, the R rows of a block contiguous
+    float     *d_bval32;        // fp32 copy, made on the first fp32 exec
+    int       *d_rest;          // nrest: row ids for the row-split kernel
+};
 
 struct crp_spmm_plan
 {
@@ -49,8 +65,11 @@ struct crp_spmm_plan
     // merge-path (nnz-balanced) decomposition, built on demand
     int       *d_mp_rowstart;   // per work item: first row
     int       mp_items, mp_chunk;
-    // row-block local-CSC structures (see spmm_rowblock.cu), built on demand
-    void      *rowblock;
+    crp_rowgroup rg;
+    char      kernel_name[64];
 };
+
+void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val);
+void crp_rowgroup_destroy(crp_spmm_plan *plan);
 
 #endif

@@ -9,9 +9,11 @@
 
 template <typename T, int VECN>
 void crp_launch_rowsplit(
-    const crp_spmm_plan *plan, const T *val, const int n, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
+    const crp_spmm_plan *plan, const int nrows, const int *row_list, const T *val, const int n, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
     T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
 );
+template <typename T, int VEC>
+void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s);
 
 extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int x0_rows, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint)
 {
@@ -38,6 +40,7 @@ extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, co
         CRP_CUDA_CHECK(cudaMemcpy(p->d_colidx, colidx_h, sizeof(int) * (size_t) p->nnz, cudaMemcpyHostToDevice));
         CRP_CUDA_CHECK(cudaMemcpy(p->d_val, val_h, sizeof(double) * (size_t) p->nnz, cudaMemcpyHostToDevice));
     }
+    crp_rowgroup_build(p, rowptr_h, colidx_h, val_h);
     return p;
 }
 
@@ -49,6 +52,7 @@ extern "C" void crp_cuda_spmm_plan_destroy(crp_spmm_plan *plan)
     if (plan->d_val)    CRP_CUDA_CHECK(cudaFree(plan->d_val));
     if (plan->d_val32)  CRP_CUDA_CHECK(cudaFree(plan->d_val32));
     if (plan->d_mp_rowstart) CRP_CUDA_CHECK(cudaFree(plan->d_mp_rowstart));
+    crp_rowgroup_destroy(plan);
     free(plan);
 }
 
@@ -58,14 +62,39 @@ __global__ void __launch_bounds__(256) cast_f64_to_f32_kernel(const double *__re
         dst[i] = (float) src[i];
 }
 
-static void ensure_val32(crp_spmm_plan *plan, cudaStream_t stream)
+static void cast_to_f32(const double *src, float **dst, size_t count, cudaStream_t stream)
 {
-    if (plan->d_val32 != NULL || plan->nnz == 0) return;
-    CRP_CUDA_CHECK(cudaMalloc((void **) &plan->d_val32, sizeof(float) * (size_t) plan->nnz));
-    size_t blocks = ((size_t) plan->nnz + 255) / 256;
+    if (*dst != NULL || count == 0) return;
+    CRP_CUDA_CHECK(cudaMalloc((void **) dst, sizeof(float) * count));
+    size_t blocks = (count + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    cast_f64_to_f32_kernel<<<(unsigned) blocks, 256, 0, stream>>>(plan->d_val, plan->d_val32, (size_t) plan->nnz);
+    cast_f64_to_f32_kernel<<<(unsigned) blocks, 256, 0, stream>>>(src, *dst, count);
     CRP_LAUNCH_CHECK();
+}
+
+template <typename T, int VECN>
+static void spmm_dispatch(
+    crp_spmm_plan *plan, const T *val, const T *bval, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1,
+    T alpha, T beta, T *C, size_t ldc, cudaStream_t s, const char *tname
+)
+{
+    const int x0_rows = plan->x0_rows;
+    const crp_rowgroup *rg = &plan->rg;
+    const bool want_rg = (plan->variant == CRP_VARIANT_AUTO || plan->variant == CRP_VARIANT_ROWGROUP);
+    if (want_rg && rg->R > 1 && rg->ngroups > 0 && beta == (T) 0)
+    {
+        const uintptr_t ptrs = (uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C;
+        const bool vec_ok = (n % VECN == 0) && (ldx0 % VECN == 0) && (X1 == NULL || ldx1 % VECN == 0) && (ldc % VECN == 0) && ((ptrs & 15) == 0);
+        if (vec_ok) crp_launch_rowgroup<T, VECN>(rg, bval, n / VECN, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s);
+        else        crp_launch_rowgroup<T, 1>(rg, bval, n, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s);
+        if (rg->nrest > 0)
+            crp_launch_rowsplit<T, VECN>(plan, rg->nrest, rg->d_rest, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
+        snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowgroup_%s_R%d%s", tname, rg->R, rg->nrest > 0 ? "+rowsplit" : "");
+    } else {
+        crp_launch_rowsplit<T, VECN>(plan, plan->m, NULL, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
+        snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowsplit_%s", tname);
+    }
+    plan->last_kernel = plan->kernel_name;
 }
 
 extern "C" void crp_cuda_spmm_exec(
@@ -74,20 +103,18 @@ extern "C" void crp_cuda_spmm_exec(
     const double beta, void *C, const int ldc, void *stream
 )
 {
-    const int x0_rows = plan ? plan->x0_rows : 0;
     if (plan == NULL) { fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: NULL plan\n"); abort(); }
     if (plan->m == 0 || n <= 0) return;
     cudaStream_t s = as_stream(stream);
     if (elem_size == 8)
     {
-        plan->last_kernel = "spmm_rowsplit_f64";
-        crp_launch_rowsplit<double, 2>(plan, plan->d_val, n, (const double *) X0, (size_t) ldx0, x0_rows, (const double *) X1, (size_t) ldx1,
-                                       alpha, beta, (double *) C, (size_t) ldc, s);
+        spmm_dispatch<double, 2>(plan, plan->d_val, plan->rg.d_bval, n, (const double *) X0, (size_t) ldx0, (const double *) X1, (size_t) ldx1,
+                                 alpha, beta, (double *) C, (size_t) ldc, s, "f64");
     } else if (elem_size == 4) {
-        ensure_val32(plan, s);
-        plan->last_kernel = "spmm_rowsplit_f32";
-        crp_launch_rowsplit<float, 4>(plan, plan->d_val32, n, (const float *) X0, (size_t) ldx0, x0_rows, (const float *) X1, (size_t) ldx1,
-                                      (float) alpha, (float) beta, (float *) C, (size_t) ldc, s);
+        cast_to_f32(plan->d_val, &plan->d_val32, (size_t) plan->nnz, s);
+        cast_to_f32(plan->rg.d_bval, &plan->rg.d_bval32, (size_t) plan->rg.nblk * (size_t) plan->rg.R, s);
+        spmm_dispatch<float, 4>(plan, plan->d_val32, plan->rg.d_bval32, n, (const float *) X0, (size_t) ldx0, (const float *) X1, (size_t) ldx1,
+                                (float) alpha, (float) beta, (float *) C, (size_t) ldc, s, "f32");
     } else {
         fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: elem_size must be 4 or 8\n");
         abort();
@@ -100,7 +127,7 @@ extern "C" void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name)
 {
     if (plan == NULL || name == NULL) return;
     if (strcmp(name, "rowsplit") == 0) plan->variant = CRP_VARIANT_ROWSPLIT;
-    else if (strcmp(name, "rowblock") == 0) plan->variant = CRP_VARIANT_ROWBLOCK;
+    else if (strcmp(name, "rowgroup") == 0) plan->variant = CRP_VARIANT_ROWGROUP;
     else if (strcmp(name, "mergepath") == 0) plan->variant = CRP_VARIANT_MERGEPATH;
     else plan->variant = CRP_VARIANT_AUTO;
 }

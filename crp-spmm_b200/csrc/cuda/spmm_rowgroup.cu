@@ -1,0 +1,346 @@
+// spmm_rowgroup.cu - register-blocked CSR x dense kernel for matrices whose consecutive
+// rows share their column pattern (FEM / multi-dof matrices such as pwtk: 6 unknowns per node).
+//
+// Replaces the mkl_sparse_d_mm call at reference src/rowpara_spmm.c:404-407 for such matrices.
+//
+// Why: the plain row-split kernel (spmm_rowsplit.cu) issues one B-row load per nonzero, so it
+// moves nnz * n * s bytes through L1 (24.4 GB for the pwtk-shaped n = 256 case, 23x the
+// compulsory HBM traffic) and is bound by L1/L2 throughput at a few % of the HBM roofline.
+// Here a group of R consecutive rows whose column sets are identical is stored as a list of
+// R x 1 column blocks; one B-row segment is loaded ONCE per block and reused from registers for
+// all R rows: L1 traffic drops by R and the inner loop becomes R FMAs per loaded value.
+// Groups that do not have this structure are left to the row-split kernel (no explicit zeros
+// are ever multiplied, so results on Inf / NaN inputs are the reference's).
+//
+// Mapping: a group is owned by LPR lanes (a full warp for wide dense matrices); each lane keeps
+// R x U 128-bit accumulators (U * LPR * 16 bytes of every C row of the group).  Per block the
+// lanes issue U coalesced 128-bit read-only loads of the B row and broadcast loads of the R
+// values; two blocks are in flight per iteration and the column indices of the next iteration
+// are prefetched so that the index -> address -> load chain is off the critical path.
+// C is written once with streaming stores.  Bound: fp64 FMA issue and L1/L2 gather bandwidth
+// for fp64 n = 256, HBM for A / first touch of B / C.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "crp_cuda_internal.cuh"
+
+// ------------------------------------------------------------------ plan-time analysis (host)
+
+static const int kCandR[] = { 8, 6, 4, 3, 2 };
+
+// For a group size R: which groups are "perfect" (every row of the group has exactly the same
+// sorted column list) and what the modelled cost is.  Cost unit: L1 wavefronts per 64 B of C row
+// (4 per B-row load + 1 per row FMA'd), see DESIGN.md "row-group kernel".
+static double analyse_R(const int m, const int *rowptr, const int *colidx, const int R, std::vector<unsigned char> *perfect_out, long long *nblk_out, long long *rest_nnz_out)
+{
+    const int ng = (m + R - 1) / R;
+    std::vector<unsigned char> perfect((size_t) ng, 0);
+    long long nblk = 0, rest = 0;
+    for (int g = 0; g < ng; g++)
+    {
+        const int r0 = g * R, r1 = std::min(m, r0 + R);
+        const int len = rowptr[r0 + 1] - rowptr[r0];
+        bool ok = (r1 - r0 == R) && len > 0;
+        for (int r = r0 + 1; ok && r < r1; r++)
+        {
+            if (rowptr[r + 1] - rowptr[r] != len) { ok = false; break; }
+            if (memcmp(colidx + rowptr[r], colidx + rowptr[r0], sizeof(int) * (size_t) len) != 0) ok = false;
+        }
+        if (ok)
+        {
+            // the column list must be strictly increasing for the block order to be well defined
+            for (int p = rowptr[r0] + 1; p < rowptr[r0 + 1]; p++) if (colidx[p] <= colidx[p - 1]) { ok = false; break; }
+        }
+        perfect[(size_t) g] = ok ? 1 : 0;
+        if (ok) nblk += len;
+        else rest += rowptr[r1] - rowptr[r0];
+    }
+    if (perfect_out) perfect_out->swap(perfect);
+    *nblk_out = nblk;
+    *rest_nnz_out = rest;
+    return (double) nblk * (4.0 + R) + (double) rest * 5.0;
+}
+
+void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val)
+{
+    crp_rowgroup *rg = &plan->rg;
+    memset(rg, 0, sizeof(*rg));
+    const int m = plan->m;
+    if (m == 0 || plan->nnz == 0) return;
+    int forced = 0;
+    if (const char *e = getenv("CRP_SPMM_ROWGROUP_R")) forced = atoi(e);      // 0 auto, 1 disable, else force R
+    if (forced == 1) return;
+    double best_cost = (double) plan->nnz * 5.0;      // everything in the row-split kernel
+    int best_R = 1;
+    for (int R : kCandR)
+    {
+        if (forced > 1 && R != forced) continue;
+        long long nblk, rest;
+        const double cost = analyse_R(m, rowptr, colidx, R, NULL, &nblk, &rest);
+        if ((forced > 1 && nblk > 0) || cost < 0.9 * best_cost) { best_cost = cost; best_R = R; if (forced > 1) break; }
+    }
+    if (best_R == 1) return;
+
+    const int R = best_R;
+    std::vector<unsigned char> perfect;
+    long long nblk, rest;
+    analyse_R(m, rowptr, colidx, R, &perfect, &nblk, &rest);
+    const int ng_all = (m + R - 1) / R;
+    std::vector<int> g_row, g_ptr, b_col, rest_rows;
+    std::vector<double> b_val;
+    g_ptr.push_back(0);
+    b_col.reserve((size_t) nblk);
+    b_val.reserve((size_t) nblk * R);
+    for (int g = 0; g < ng_all; g++)
+    {
+        const int r0 = g * R, r1 = std::min(m, r0 + R);
+        if (!perfect[(size_t) g])
+        {
+            for (int r = r0; r < r1; r++) rest_rows.push_back(r);
+            continue;
+        }
+        g_row.push_back(r0);
+        const int len = rowptr[r0 + 1] - rowptr[r0];
+        for (int j = 0; j < len; j++)
+        {
+            b_col.push_back(colidx[rowptr[r0] + j]);
+            for (int r = 0; r < R; r++) b_val.push_back(val[rowptr[r0 + r] + j]);
+        }
+        g_ptr.push_back((int) b_col.size());
+    }
+    rg->R = R;
+    rg->ngroups = (int) g_row.size();
+    rg->nblk = (long long) b_col.size();
+    rg->nrest = (int) rest_rows.size();
+    rg->rest_nnz = rest;
+    auto upload = [](const void *src, size_t bytes) -> void * {
+        void *d = NULL;
+        if (bytes == 0) return d;
+        CRP_CUDA_CHECK(cudaMalloc(&d, bytes));
+        CRP_CUDA_CHECK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        return d;
+    };
+    rg->d_grow = (int *) upload(g_row.data(), sizeof(int) * g_row.size());
+    rg->d_gptr = (int *) upload(g_ptr.data(), sizeof(int) * g_ptr.size());
+    rg->d_bcol = (int *) upload(b_col.data(), sizeof(int) * b_col.size());
+    rg->d_bval = (double *) upload(b_val.data(), sizeof(double) * b_val.size());
+    rg->d_rest = (int *) upload(rest_rows.data(), sizeof(int) * rest_rows.size());
+}
+
+void crp_rowgroup_destroy(crp_spmm_plan *plan)
+{
+    crp_rowgroup *rg = &plan->rg;
+    if (rg->d_grow) CRP_CUDA_CHECK(cudaFree(rg->d_grow));
+    if (rg->d_gptr) CRP_CUDA_CHECK(cudaFree(rg->d_gptr));
+    if (rg->d_bcol) CRP_CUDA_CHECK(cudaFree(rg->d_bcol));
+    if (rg->d_bval) CRP_CUDA_CHECK(cudaFree(rg->d_bval));
+    if (rg->d_bval32) CRP_CUDA_CHECK(cudaFree(rg->d_bval32));
+    if (rg->d_rest) CRP_CUDA_CHECK(cudaFree(rg->d_rest));
+    memset(rg, 0, sizeof(*rg));
+}
+
+// ------------------------------------------------------------------------------- kernel
+
+template <typename T> struct vec128;
+template <> struct vec128<double> { typedef double2 type; static constexpr int N = 2; };
+template <> struct vec128<float>  { typedef float4  type; static constexpr int N = 4; };
+
+template <typename T, int VEC> struct xload;
+template <> struct xload<double, 2>
+{
+    static __device__ __forceinline__ void ld(const double *p, double (&v)[2]) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void st(double *p, const double (&v)[2]) { __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1])); }
+};
+template <> struct xload<float, 4>
+{
+    static __device__ __forceinline__ void ld(const float *p, float (&v)[4]) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void st(float *p, const float (&v)[4]) { __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <typename T> struct xload<T, 1>
+{
+    static __device__ __forceinline__ void ld(const T *p, T (&v)[1]) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void st(T *p, const T (&v)[1]) { __stcs(p, v[0]); }
+};
+
+// the R values of one block: 128-bit broadcast loads where the block stride allows it
+template <typename T, int R>
+__device__ __forceinline__ void load_block_vals(const T *__restrict__ p, T (&a)[R])
+{
+    constexpr int PER16 = 16 / (int) sizeof(T);
+    if constexpr ((R % PER16) == 0)
+    {
+        #pragma unroll
+        for (int i = 0; i < R / PER16; i++)
+        {
+            const typename vec128<T>::type t = __ldg(reinterpret_cast<const typename vec128<T>::type *>(p) + i);
+            const T *tp = reinterpret_cast<const T *>(&t);
+            #pragma unroll
+            for (int e = 0; e < PER16; e++) a[i * PER16 + e] = tp[e];
+        }
+    } else if constexpr (sizeof(T) == 4 && (R % 2) == 0) {
+        #pragma unroll
+        for (int i = 0; i < R / 2; i++)
+        {
+            const float2 t = __ldg(reinterpret_cast<const float2 *>(p) + i);
+            a[2 * i] = t.x; a[2 * i + 1] = t.y;
+        }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < R; i++) a[i] = __ldg(p + i);
+    }
+}
+
+template <typename T, int VEC, int R, int LPR, int U>
+__global__ void __launch_bounds__(256) spmm_rowgroup_kernel(
+    const int ngroups, const int *__restrict__ grow, const int *__restrict__ gptr,
+    const int *__restrict__ bcol, const T *__restrict__ bval,
+    const int nv,                                   // VEC-wide column groups per dense row
+    const T *__restrict__ X0, const size_t ldx0, const int x0_rows,
+    const T *__restrict__ X1, const size_t ldx1,
+    const T alpha, T *__restrict__ C, const size_t ldc
+)
+{
+    constexpr int GW = 32 / LPR;                    // groups per warp
+    constexpr int NB = 2;                           // blocks in flight per iteration
+    const int warp = (int) ((blockIdx.x * (unsigned) blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int g = warp * GW + lane / LPR;
+    const int l = lane % LPR;
+    const int v0 = blockIdx.y * (LPR * U);          // first column group of this CTA's column chunk
+    int p = 0, p_end = 0, row0 = 0;
+    if (g < ngroups) { p = __ldg(gptr + g); p_end = __ldg(gptr + g + 1); row0 = __ldg(grow + g); }
+
+    int voff[U];                                    // element offset of this lane's column groups; -1: beyond n
+    #pragma unroll
+    for (int u = 0; u < U; u++) { const int v = v0 + u * LPR + l; voff[u] = (v < nv) ? v * VEC : -1; }
+
+    T acc[R][U][VEC];
+    #pragma unroll
+    for (int r = 0; r < R; r++)
+        #pragma unroll
+        for (int u = 0; u < U; u++)
+            #pragma unroll
+            for (int e = 0; e < VEC; e++) acc[r][u][e] = (T) 0;
+
+    int cn[NB];
+    #pragma unroll
+    for (int q = 0; q < NB; q++) cn[q] = (p + q < p_end) ? __ldg(bcol + p + q) : 0;
+
+    for (; p + NB <= p_end; p += NB)
+    {
+        int c[NB];
+        #pragma unroll
+        for (int q = 0; q < NB; q++) c[q] = cn[q];
+        #pragma unroll
+        for (int q = 0; q < NB; q++) cn[q] = (p + NB + q < p_end) ? __ldg(bcol + p + NB + q) : 0;
+        T x[NB][U][VEC], a[NB][R];
+        #pragma unroll
+        for (int q = 0; q < NB; q++)
+        {
+            const T *xr = (c[q] < x0_rows) ? X0 + (size_t) c[q] * ldx0 : X1 + (size_t) (c[q] - x0_rows) * ldx1;
+            #pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], x[q][u]);
+                else { for (int e = 0; e < VEC; e++) x[q][u][e] = (T) 0; }
+            }
+            load_block_vals<T, R>(bval + (size_t) (p + q) * R, a[q]);
+        }
+        #pragma unroll
+        for (int q = 0; q < NB; q++)
+            #pragma unroll
+            for (int r = 0; r < R; r++)
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                    #pragma unroll
+                    for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[q][r], x[q][u][e], acc[r][u][e]);
+    }
+    if (p < p_end)                                  // NB == 2: at most one block left, its index is in cn[0]
+    {
+        const int c = cn[0];
+        const T *xr = (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
+        T a[R];
+        load_block_vals<T, R>(bval + (size_t) p * R, a);
+        #pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            if (voff[u] < 0) continue;
+            T x[VEC];
+            xload<T, VEC>::ld(xr + voff[u], x);
+            #pragma unroll
+            for (int r = 0; r < R; r++)
+                #pragma unroll
+                for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], x[e], acc[r][u][e]);
+        }
+    }
+
+    if (g < ngroups)
+    {
+        #pragma unroll
+        for (int r = 0; r < R; r++)
+        {
+            T *crow = C + (size_t) (row0 + r) * ldc;
+            #pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (voff[u] < 0) continue;
+                T out[VEC];
+                #pragma unroll
+                for (int e = 0; e < VEC; e++) out[e] = alpha * acc[r][u][e];
+                xload<T, VEC>::st(crow + voff[u], out);
+            }
+        }
+    }
+}
+
+template <typename T, int VEC, int R, int LPR, int U>
+static void rg_launch_one(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
+{
+    constexpr int GW = 32 / LPR;
+    const long long warps = ((long long) rg->ngroups + GW - 1) / GW;
+    const unsigned blocks = (unsigned) ((warps + 7) / 8);
+    const unsigned chunks = (unsigned) ((nv + LPR * U - 1) / (LPR * U));
+    if (blocks == 0) return;
+    spmm_rowgroup_kernel<T, VEC, R, LPR, U><<<dim3(blocks, chunks), 256, 0, s>>>(
+        rg->ngroups, rg->d_grow, rg->d_gptr, rg->d_bcol, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc);
+    CRP_LAUNCH_CHECK();
+}
+
+template <typename T, int VEC, int R>
+static void rg_launch_R(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
+{
+    constexpr int UMAX = (R * VEC * (int) sizeof(T) <= 6 * 16) ? 4 : 2;       // keep the accumulator tile <= 96 registers
+#define CRP_RG(LPR, U) rg_launch_one<T, VEC, R, LPR, U>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)
+    static int umax_env = -1;                       // CRP_SPMM_RG_U: cap on the 128-bit accumulators per lane and row (tuning aid)
+    if (umax_env < 0) { const char *e = getenv("CRP_SPMM_RG_U"); umax_env = e ? atoi(e) : 0; }
+    const int umax = (umax_env > 0 && umax_env < UMAX) ? umax_env : UMAX;
+    if (nv >= 128 && umax >= 4) CRP_RG(32, 4);
+    else if (nv >= 64 && umax >= 2) CRP_RG(32, 2);
+    else if (nv > 16)           CRP_RG(32, 1);
+    else if (nv > 8)            CRP_RG(16, 1);
+    else if (nv > 4)            CRP_RG(8, 1);
+    else                        CRP_RG(4, 1);
+#undef CRP_RG
+}
+
+template <typename T, int VEC>
+void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
+{
+#define CRP_RGR(R) rg_launch_R<T, VEC, R>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)
+    switch (rg->R)
+    {
+        case 2: CRP_RGR(2); break;
+        case 3: CRP_RGR(3); break;
+        case 4: CRP_RGR(4); break;
+        case 6: CRP_RGR(6); break;
+        case 8: CRP_RGR(8); break;
+        default: fprintf(stderr, "[FATAL] crp_launch_rowgroup: unsupported group size %d\n", rg->R); abort();
+    }
+#undef CRP_RGR
+}
+
+template void crp_launch_rowgroup<double, 2>(const crp_rowgroup *, const double *, int, const double *, size_t, int, const double *, size_t, double, double *, size_t, cudaStream_t);
+template void crp_launch_rowgroup<double, 1>(const crp_rowgroup *, const double *, int, const double *, size_t, int, const double *, size_t, double, double *, size_t, cudaStream_t);
+template void crp_launch_rowgroup<float, 4>(const crp_rowgroup *, const float *, int, const float *, size_t, int, const float *, size_t, float, float *, size_t, cudaStream_t);
+template void crp_launch_rowgroup<float, 1>(const crp_rowgroup *, const float *, int, const float *, size_t, int, const float *, size_t, float, float *, size_t, cudaStream_t);

@@ -113,7 +113,7 @@ void crp_cuda_spmm_exec(
 );
 /* name of the kernel variant the last crp_cuda_spmm_exec on this plan launched (static string) */
 const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan);
-/* force a kernel variant for experiments: "auto", "rowsplit", "rowblock", "mergepath" */
+/* force a kernel variant for experiments: "auto", "rowsplit", "rowgroup", "mergepath" */
 void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name);
 
 /* Host-in / host-out convenience with the deprecated proxy's argument list:

@@ -31,7 +31,7 @@ unsigned long long crp_nccl_group_count(void);
 
 /* Name of the local-SpMM kernel variant the engine's last exec launched. */
 const char *rp_spmm_kernel_name(rp_spmm_p rp_spmm);
-/* Force a variant ("auto", "rowsplit", "rowblock", "mergepath") for experiments. */
+/* Force a variant ("auto", "rowsplit", "rowgroup", "mergepath") for experiments. */
 void rp_spmm_set_kernel(rp_spmm_p rp_spmm, const char *name);
 
 /* Device time (seconds since the last clear_stat) spent staging a host B in / a host C out. */
