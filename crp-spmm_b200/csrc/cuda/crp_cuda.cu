@@ -179,6 +179,15 @@ extern "C" void *crp_cuda_event_create(void)
 extern "C" void crp_cuda_event_destroy(void *event) { if (event) CRP_CUDA_CHECK(cudaEventDestroy((cudaEvent_t) event)); }
 extern "C" void crp_cuda_event_record(void *event, void *stream) { CRP_CUDA_CHECK(cudaEventRecord((cudaEvent_t) event, as_stream(stream))); }
 extern "C" void crp_cuda_event_sync(void *event) { CRP_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t) event)); }
+extern "C" int crp_cuda_event_done(void *event)
+{
+    cudaError_t err = cudaEventQuery((cudaEvent_t) event);
+    if (err == cudaSuccess) return 1;
+    if (err == cudaErrorNotReady) return 0;
+    CRP_CUDA_CHECK(err);
+    return 0;
+}
+
 extern "C" void crp_cuda_stream_wait_event(void *stream, void *event) { CRP_CUDA_CHECK(cudaStreamWaitEvent(as_stream(stream), (cudaEvent_t) event, 0)); }
 
 extern "C" float crp_cuda_event_elapsed_ms(void *start, void *stop)

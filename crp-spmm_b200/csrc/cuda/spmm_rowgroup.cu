@@ -191,8 +191,52 @@ __device__ __forceinline__ void load_block_vals(const T *__restrict__ p, T (&a)[
     }
 }
 
-template <typename T, int VEC, int R, int LPR, int U>
-__global__ void __launch_bounds__(256) spmm_rowgroup_kernel(
+// one stage of the software pipeline: NB blocks' worth of B-row segments and values
+template <typename T, int VEC, int R, int U, int NB>
+struct rg_stage
+{
+    T x[NB][U][VEC];
+    T a[NB][R];
+};
+
+template <typename T, int VEC, int R, int U, int NB>
+__device__ __forceinline__ void rg_load_stage(
+    rg_stage<T, VEC, R, U, NB> &st, const int (&c)[NB], const int p, const T *__restrict__ bval, const int (&voff)[U],
+    const T *__restrict__ X0, const size_t ldx0, const int x0_rows, const T *__restrict__ X1, const size_t ldx1
+)
+{
+    #pragma unroll
+    for (int q = 0; q < NB; q++)
+    {
+        const T *xr = (c[q] < x0_rows) ? X0 + (size_t) c[q] * ldx0 : X1 + (size_t) (c[q] - x0_rows) * ldx1;
+        #pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], st.x[q][u]);
+            else { for (int e = 0; e < VEC; e++) st.x[q][u][e] = (T) 0; }
+        }
+        load_block_vals<T, R>(bval + (size_t) (p + q) * R, st.a[q]);
+    }
+}
+
+template <typename T, int VEC, int R, int U, int NB>
+__device__ __forceinline__ void rg_fma_stage(const rg_stage<T, VEC, R, U, NB> &st, T (&acc)[R][U][VEC])
+{
+    #pragma unroll
+    for (int q = 0; q < NB; q++)
+        #pragma unroll
+        for (int r = 0; r < R; r++)
+            #pragma unroll
+            for (int u = 0; u < U; u++)
+                #pragma unroll
+                for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(st.a[q][r], st.x[q][u][e], acc[r][u][e]);
+}
+
+// PIPE = 1: the loads of the next NB blocks are issued before the FMAs of the current ones (register
+// double buffering).  PF > 0: the B rows of the blocks PF positions ahead are prefetched into L1
+// (CCTL.E.PF1, one 128-byte line per lane), which keeps gathers in flight without holding registers.
+template <typename T, int VEC, int R, int LPR, int U, int NB, int PIPE, int PF, int BS>
+__global__ void __launch_bounds__(BS) spmm_rowgroup_kernel(
     const int ngroups, const int *__restrict__ grow, const int *__restrict__ gptr,
     const int *__restrict__ bcol, const T *__restrict__ bval,
     const int nv,                                   // VEC-wide column groups per dense row
@@ -202,7 +246,6 @@ __global__ void __launch_bounds__(256) spmm_rowgroup_kernel(
 )
 {
     constexpr int GW = 32 / LPR;                    // groups per warp
-    constexpr int NB = 2;                           // blocks in flight per iteration
     const int warp = (int) ((blockIdx.x * (unsigned) blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     const int g = warp * GW + lane / LPR;
@@ -223,45 +266,92 @@ __global__ void __launch_bounds__(256) spmm_rowgroup_kernel(
             #pragma unroll
             for (int e = 0; e < VEC; e++) acc[r][u][e] = (T) 0;
 
+    // L1 prefetch: lane l covers bytes [128 l, 128 l + 128) of the CTA's column chunk of a B row
+    constexpr int CHUNK_BYTES = LPR * U * VEC * (int) sizeof(T);
+    const int pf_off = (v0 * VEC * (int) sizeof(T)) + l * 128;
+    const bool pf_lane = (PF > 0) && (l * 128 < CHUNK_BYTES) && (v0 * VEC + l * (128 / (int) sizeof(T)) < nv * VEC);
+    auto prefetch_row = [&](const int pp) {
+        if (PF > 0 && pp < p_end && pf_lane)
+        {
+            const int c = __ldg(bcol + pp);
+            const char *xr = (c < x0_rows) ? (const char *) (X0 + (size_t) c * ldx0) : (const char *) (X1 + (size_t) (c - x0_rows) * ldx1);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(xr + pf_off));
+        }
+    };
+    if (PF > 0)
+    {
+        #pragma unroll 1
+        for (int d = 0; d < PF; d++) prefetch_row(p + d);
+    }
+
+    typedef rg_stage<T, VEC, R, U, NB> stage_t;
     int cn[NB];
     #pragma unroll
     for (int q = 0; q < NB; q++) cn[q] = (p + q < p_end) ? __ldg(bcol + p + q) : 0;
 
-    for (; p + NB <= p_end; p += NB)
+    if (PIPE == 0)
     {
-        int c[NB];
-        #pragma unroll
-        for (int q = 0; q < NB; q++) c[q] = cn[q];
-        #pragma unroll
-        for (int q = 0; q < NB; q++) cn[q] = (p + NB + q < p_end) ? __ldg(bcol + p + NB + q) : 0;
-        T x[NB][U][VEC], a[NB][R];
-        #pragma unroll
-        for (int q = 0; q < NB; q++)
+        for (; p + NB <= p_end; p += NB)
         {
-            const T *xr = (c[q] < x0_rows) ? X0 + (size_t) c[q] * ldx0 : X1 + (size_t) (c[q] - x0_rows) * ldx1;
+            int c[NB];
             #pragma unroll
-            for (int u = 0; u < U; u++)
-            {
-                if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], x[q][u]);
-                else { for (int e = 0; e < VEC; e++) x[q][u][e] = (T) 0; }
-            }
-            load_block_vals<T, R>(bval + (size_t) (p + q) * R, a[q]);
+            for (int q = 0; q < NB; q++) c[q] = cn[q];
+            #pragma unroll
+            for (int q = 0; q < NB; q++) cn[q] = (p + NB + q < p_end) ? __ldg(bcol + p + NB + q) : 0;
+            #pragma unroll
+            for (int q = 0; q < NB; q++) prefetch_row(p + PF + q);
+            stage_t st;
+            rg_load_stage<T, VEC, R, U, NB>(st, c, p, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
+            rg_fma_stage<T, VEC, R, U, NB>(st, acc);
         }
-        #pragma unroll
-        for (int q = 0; q < NB; q++)
+    } else {
+        stage_t sa, sb;
+        bool have_a = false;
+        if (p + NB <= p_end)
+        {
+            rg_load_stage<T, VEC, R, U, NB>(sa, cn, p, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
+            have_a = true;
             #pragma unroll
-            for (int r = 0; r < R; r++)
+            for (int q = 0; q < NB; q++) cn[q] = (p + NB + q < p_end) ? __ldg(bcol + p + NB + q) : 0;
+        }
+        // invariant: sa holds blocks [p, p + NB), cn the columns of [p + NB, p + 2 NB)
+        while (have_a)
+        {
+            const bool next_b = (p + 2 * NB <= p_end);
+            if (next_b)
+            {
+                rg_load_stage<T, VEC, R, U, NB>(sb, cn, p + NB, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
                 #pragma unroll
-                for (int u = 0; u < U; u++)
-                    #pragma unroll
-                    for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[q][r], x[q][u][e], acc[r][u][e]);
+                for (int q = 0; q < NB; q++) cn[q] = (p + 2 * NB + q < p_end) ? __ldg(bcol + p + 2 * NB + q) : 0;
+            }
+            #pragma unroll
+            for (int q = 0; q < NB; q++) prefetch_row(p + PF + q);
+            rg_fma_stage<T, VEC, R, U, NB>(sa, acc);
+            p += NB;
+            if (!next_b) break;
+            const bool next_a = (p + 2 * NB <= p_end);
+            if (next_a)
+            {
+                rg_load_stage<T, VEC, R, U, NB>(sa, cn, p + NB, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
+                #pragma unroll
+                for (int q = 0; q < NB; q++) cn[q] = (p + 2 * NB + q < p_end) ? __ldg(bcol + p + 2 * NB + q) : 0;
+            }
+            #pragma unroll
+            for (int q = 0; q < NB; q++) prefetch_row(p + PF + q);
+            rg_fma_stage<T, VEC, R, U, NB>(sb, acc);
+            p += NB;
+            have_a = next_a;
+        }
     }
-    if (p < p_end)                                  // NB == 2: at most one block left, its index is in cn[0]
+    // fewer than NB blocks left; cn[] holds their columns
+    #pragma unroll
+    for (int q = 0; q < NB - 1; q++)
     {
-        const int c = cn[0];
+        if (p + q >= p_end) break;
+        const int c = cn[q];
         const T *xr = (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
         T a[R];
-        load_block_vals<T, R>(bval + (size_t) p * R, a);
+        load_block_vals<T, R>(bval + (size_t) (p + q) * R, a);
         #pragma unroll
         for (int u = 0; u < U; u++)
         {
@@ -294,29 +384,60 @@ __global__ void __launch_bounds__(256) spmm_rowgroup_kernel(
     }
 }
 
-template <typename T, int VEC, int R, int LPR, int U>
+template <typename T, int VEC, int R, int LPR, int U, int NB = 2, int PIPE = 0, int PF = 0, int BS = 256>
 static void rg_launch_one(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
 {
     constexpr int GW = 32 / LPR;
     const long long warps = ((long long) rg->ngroups + GW - 1) / GW;
-    const unsigned blocks = (unsigned) ((warps + 7) / 8);
+    const unsigned blocks = (unsigned) ((warps + BS / 32 - 1) / (BS / 32));
     const unsigned chunks = (unsigned) ((nv + LPR * U - 1) / (LPR * U));
     if (blocks == 0) return;
-    spmm_rowgroup_kernel<T, VEC, R, LPR, U><<<dim3(blocks, chunks), 256, 0, s>>>(
+    spmm_rowgroup_kernel<T, VEC, R, LPR, U, NB, PIPE, PF, BS><<<dim3(blocks, chunks), BS, 0, s>>>(
         rg->ngroups, rg->d_grow, rg->d_gptr, rg->d_bcol, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc);
     CRP_LAUNCH_CHECK();
+}
+
+// development sweep (CRP_SPMM_RG_CFG = index): fp64, 128-bit, R = 6, full-warp groups only
+template <typename T, int VEC, int R>
+static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
+{
+    if constexpr (sizeof(T) == 8 && VEC == 2 && R == 6)
+    {
+        const char *e = getenv("CRP_SPMM_RG_CFG");
+        if (e == NULL || nv < 128) return false;
+#define CRP_RGX(U, NB, PIPE, PF, BS) rg_launch_one<T, VEC, R, 32, U, NB, PIPE, PF, BS>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s); return true
+        switch (atoi(e))
+        {
+            case 0:  CRP_RGX(4, 2, 0, 0, 256);
+            case 1:  CRP_RGX(4, 2, 0, 0, 128);
+            case 2:  CRP_RGX(2, 2, 0, 0, 256);
+            case 3:  CRP_RGX(2, 4, 0, 0, 256);
+            case 4:  CRP_RGX(4, 1, 1, 0, 128);
+            case 5:  CRP_RGX(4, 2, 0, 8, 128);
+            case 6:  CRP_RGX(2, 2, 1, 0, 128);
+            case 7:  CRP_RGX(2, 2, 0, 8, 256);
+            case 8:  CRP_RGX(1, 4, 0, 0, 256);
+            case 9:  CRP_RGX(4, 1, 1, 8, 128);
+            case 10: CRP_RGX(2, 4, 0, 16, 256);
+            case 11: CRP_RGX(1, 4, 0, 16, 256);
+            case 12: CRP_RGX(4, 1, 0, 8, 128);
+            case 13: CRP_RGX(2, 1, 1, 0, 256);
+            default: return false;
+        }
+#undef CRP_RGX
+    }
+    return false;
 }
 
 template <typename T, int VEC, int R>
 static void rg_launch_R(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
 {
+    if (rg_launch_experiment<T, VEC, R>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)) return;
     constexpr int UMAX = (R * VEC * (int) sizeof(T) <= 6 * 16) ? 4 : 2;       // keep the accumulator tile <= 96 registers
 #define CRP_RG(LPR, U) rg_launch_one<T, VEC, R, LPR, U>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)
-    static int umax_env = -1;                       // CRP_SPMM_RG_U: cap on the 128-bit accumulators per lane and row (tuning aid)
-    if (umax_env < 0) { const char *e = getenv("CRP_SPMM_RG_U"); umax_env = e ? atoi(e) : 0; }
-    const int umax = (umax_env > 0 && umax_env < UMAX) ? umax_env : UMAX;
-    if (nv >= 128 && umax >= 4) CRP_RG(32, 4);
-    else if (nv >= 64 && umax >= 2) CRP_RG(32, 2);
+    // 128-thread CTAs for the widest tile: 168 registers per thread -> 3 CTAs (12 warps) per SM instead of 8 warps (measured 0.72 -> 0.60 ms)
+    if (nv >= 128 && UMAX >= 4) rg_launch_one<T, VEC, R, 32, 4, 2, 0, 0, 128>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s);
+    else if (nv >= 64)          CRP_RG(32, 2);
     else if (nv > 16)           CRP_RG(32, 1);
     else if (nv > 8)            CRP_RG(16, 1);
     else if (nv > 4)            CRP_RG(8, 1);

@@ -46,6 +46,7 @@ int  *crp_comm_ranks_in_parent(MPI_Comm sub, MPI_Comm parent);
 
 /* ---- device-side state of a row-parallel engine (rowpara_spmm.c) ---- */
 enum { CRP_EV_START = 0, CRP_EV_B_IN, CRP_EV_PACKED, CRP_EV_XCHG, CRP_EV_SPMM, CRP_EV_END, CRP_RP_NEV };
+enum { CRP_RP_RING = 8 };
 
 struct crp_rp_dev
 {
@@ -64,9 +65,10 @@ struct crp_rp_dev
     void    *h_sendbuf;  size_t h_sendbuf_bytes;   /* pinned, staged-MPI transport only              */
     void    *h_recvbuf;  size_t h_recvbuf_bytes;
     void    *stream;            /* own non-blocking stream                                           */
-    void    *ev[CRP_RP_NEV];
-    int     pending;            /* events of the last exec not yet folded into the statistics        */
-    double  pending_host_t0;
+    void    *ev[CRP_RP_RING][CRP_RP_NEV];  /* ring of event sets: stats of an exec are folded in later,     */
+    double  ring_host_t0[CRP_RP_RING];     /* when its events have completed, without stalling the host     */
+    double  ring_host_t1[CRP_RP_RING];
+    int     ring_head, ring_count;
     double  t_h2d, t_d2h;       /* staging of host B / C (seconds, device time)                      */
     int     staged;             /* 1: exchange through pinned host memory + MPI (ranks share a GPU)  */
     crp_nccl_comm *nc;          /* NCCL communicator used for the B-row exchange                     */

@@ -233,7 +233,8 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
         crp_cuda_memcpy_h2d(rp->rB_sridxs, d->d_sridxs, sizeof(int) * (size_t) d->n_send_rows);
     }
     d->stream = crp_cuda_stream_create();
-    for (int i = 0; i < CRP_RP_NEV; i++) d->ev[i] = crp_cuda_event_create();
+    for (int k = 0; k < CRP_RP_RING; k++)
+        for (int i = 0; i < CRP_RP_NEV; i++) d->ev[k][i] = crp_cuda_event_create();
 
     /* transport: NCCL needs one device per rank */
     int wsize = 1;
@@ -265,7 +266,8 @@ static void rp_free_device_state(rp_spmm_p rp)
     crp_cuda_free_dev(d->d_Lwork);
     crp_cuda_free_host(d->h_sendbuf);
     crp_cuda_free_host(d->h_recvbuf);
-    for (int i = 0; i < CRP_RP_NEV; i++) crp_cuda_event_destroy(d->ev[i]);
+    for (int k = 0; k < CRP_RP_RING; k++)
+        for (int i = 0; i < CRP_RP_NEV; i++) crp_cuda_event_destroy(d->ev[k][i]);
     crp_cuda_stream_destroy(d->stream);
     free(d->send_rows);
     free(d->recv_rows);
@@ -332,19 +334,28 @@ void rp_spmm_free(rp_spmm_p *rp_spmm)
     *rp_spmm = NULL;
 }
 
-/* fold the events of the last exec into the statistics (after its stream work completed) */
-static void rp_collect(rp_spmm_p rp)
+/* Fold the events of finished execs into the statistics.  wait = 0: only those whose events
+ * have completed (never stalls the host); wait = 1: all of them (synchronises). */
+static void rp_collect(rp_spmm_p rp, const int wait)
 {
     struct crp_rp_dev *d = (struct crp_rp_dev *) rp->dev;
-    if (d == NULL || !d->pending) return;
-    crp_cuda_event_sync(d->ev[CRP_EV_END]);
-    rp->t_pack   += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_B_IN],   d->ev[CRP_EV_PACKED]);
-    rp->t_a2a    += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_PACKED], d->ev[CRP_EV_XCHG]);
-    rp->t_spmm   += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_XCHG],   d->ev[CRP_EV_SPMM]);
-    d->t_h2d     += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_START],  d->ev[CRP_EV_B_IN]);
-    d->t_d2h     += 1e-3 * crp_cuda_event_elapsed_ms(d->ev[CRP_EV_SPMM],   d->ev[CRP_EV_END]);
-    rp->t_exec   += get_wtime_sec() - d->pending_host_t0;
-    d->pending = 0;
+    if (d == NULL) return;
+    while (d->ring_count > 0)
+    {
+        const int k = (d->ring_head - d->ring_count + CRP_RP_RING) % CRP_RP_RING;      /* oldest */
+        void **ev = d->ev[k];
+        if (wait) crp_cuda_event_sync(ev[CRP_EV_END]);
+        else if (!crp_cuda_event_done(ev[CRP_EV_END])) break;
+        rp->t_pack += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_B_IN],   ev[CRP_EV_PACKED]);
+        rp->t_a2a  += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_PACKED], ev[CRP_EV_XCHG]);
+        rp->t_spmm += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_XCHG],   ev[CRP_EV_SPMM]);
+        d->t_h2d   += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_START],  ev[CRP_EV_B_IN]);
+        d->t_d2h   += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_SPMM],   ev[CRP_EV_END]);
+        /* blocking execs: host wall clock of the call; enqueue-only execs: device time start -> end */
+        if (d->ring_host_t1[k] > 0.0) rp->t_exec += d->ring_host_t1[k] - d->ring_host_t0[k];
+        else rp->t_exec += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_START], ev[CRP_EV_END]);
+        d->ring_count--;
+    }
 }
 
 /* the exchange of packed rows: device send buffer -> device receive buffer */
@@ -403,8 +414,9 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         fflush(stderr);
         abort();
     }
-    rp_collect(rp);
+    rp_collect(rp, d->ring_count == CRP_RP_RING);
     const double host_t0 = get_wtime_sec();
+    void **ev = d->ev[d->ring_head];
     const int n = rp->glb_n, m = rp->A_nrow, nB = d->nB;
     const size_t es = (size_t) elem_size;
     const size_t row_bytes = es * (size_t) n;
@@ -412,7 +424,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     const int B_on_dev = (nB > 0 && n > 0) ? crp_cuda_ptr_is_device(B) : 1;
     const int C_on_dev = (m > 0 && n > 0) ? crp_cuda_ptr_is_device(C) : 1;
 
-    crp_cuda_event_record(d->ev[CRP_EV_START], stream);
+    crp_cuda_event_record(ev[CRP_EV_START], stream);
 
     /* ---- B as a row-major device matrix Bd (leading dimension ldBd) ---- */
     const void *Bd = B;
@@ -447,7 +459,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
             ldBd = (size_t) n;
         }
     }
-    crp_cuda_event_record(d->ev[CRP_EV_B_IN], stream);
+    crp_cuda_event_record(ev[CRP_EV_B_IN], stream);
 
     /* ---- pack the rows other ranks need ---- */
     if (d->n_send_rows > 0 && n > 0)
@@ -456,11 +468,11 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         crp_cuda_gather_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, d->d_sendbuf, n, stream);
     }
     if (d->n_recv_rows > 0 && n > 0) grow_dev(&d->d_recvbuf, &d->recvbuf_bytes, row_bytes * (size_t) d->n_recv_rows);
-    crp_cuda_event_record(d->ev[CRP_EV_PACKED], stream);
+    crp_cuda_event_record(ev[CRP_EV_PACKED], stream);
 
     /* ---- exchange ---- */
     if (n > 0) rp_exchange(rp, d, row_bytes, stream);
-    crp_cuda_event_record(d->ev[CRP_EV_XCHG], stream);
+    crp_cuda_event_record(ev[CRP_EV_XCHG], stream);
 
     /* ---- local product, reading own rows from Bd and remote rows from the receive buffer ---- */
     void *Cd = C;
@@ -476,7 +488,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         }
         crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
     }
-    crp_cuda_event_record(d->ev[CRP_EV_SPMM], stream);
+    crp_cuda_event_record(ev[CRP_EV_SPMM], stream);
 
     /* ---- C back to where the caller wants it ---- */
     if (m > 0 && n > 0 && !C_direct)
@@ -494,12 +506,20 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
             crp_cuda_memcpy2d_async(d->d_Lwork, es * (size_t) m, C, es * (size_t) ldC, es * (size_t) m, (size_t) n, stream);
         }
     }
-    crp_cuda_event_record(d->ev[CRP_EV_END], stream);
+    crp_cuda_event_record(ev[CRP_EV_END], stream);
 
-    d->pending = 1;
-    d->pending_host_t0 = host_t0;
+    const int k = d->ring_head;
+    d->ring_head = (d->ring_head + 1) % CRP_RP_RING;
+    d->ring_count++;
+    d->ring_host_t0[k] = host_t0;
+    d->ring_host_t1[k] = 0.0;
     rp->n_exec++;
-    if (crp_opt_blocking() || !C_on_dev || !B_on_dev) rp_collect(rp);
+    if (crp_opt_blocking() || !C_on_dev || !B_on_dev)
+    {
+        crp_cuda_event_sync(ev[CRP_EV_END]);
+        d->ring_host_t1[k] = get_wtime_sec();
+        rp_collect(rp, 1);
+    }
 }
 
 void rp_spmm_exec(rp_spmm_p rp_spmm, const int BC_layout, const double *B, const int ldB, double *C, const int ldC)
@@ -530,7 +550,7 @@ void rp_spmm_device_times(rp_spmm_p rp, double *t_h2d, double *t_d2h)
 {
     *t_h2d = *t_d2h = 0.0;
     if (rp == NULL || rp->dev == NULL) return;
-    rp_collect(rp);
+    rp_collect(rp, 1);
     *t_h2d = ((struct crp_rp_dev *) rp->dev)->t_h2d;
     *t_d2h = ((struct crp_rp_dev *) rp->dev)->t_d2h;
 }
@@ -539,7 +559,7 @@ void rp_spmm_device_times(rp_spmm_p rp, double *t_h2d, double *t_d2h)
 void rp_spmm_print_stat(rp_spmm_p rp)
 {
     if (rp == NULL) return;
-    rp_collect(rp);
+    rp_collect(rp, 1);
     const int n_exec = rp->n_exec;
     if (n_exec == 0) return;
     unsigned long long recv_rows = (unsigned long long) rp->rB_recv_size, recv_max = 0, recv_sum = 0;
@@ -571,7 +591,7 @@ void rp_spmm_print_stat(rp_spmm_p rp)
 void rp_spmm_clear_stat(rp_spmm_p rp)
 {
     if (rp == NULL) return;
-    rp_collect(rp);
+    rp_collect(rp, 1);
     rp->n_exec   = 0;
     rp->t_pack   = 0.0;
     rp->t_a2a    = 0.0;

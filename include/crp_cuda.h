@@ -65,6 +65,7 @@ void *crp_cuda_event_create(void);
 void  crp_cuda_event_destroy(void *event);
 void  crp_cuda_event_record(void *event, void *stream);
 void  crp_cuda_event_sync(void *event);
+int   crp_cuda_event_done(void *event);            /* 1 if the event has completed (cudaEventQuery) */
 void  crp_cuda_stream_wait_event(void *stream, void *event);
 float crp_cuda_event_elapsed_ms(void *start, void *stop);
 
