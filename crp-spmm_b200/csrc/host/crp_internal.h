@@ -68,6 +68,7 @@ struct crp_rp_dev
     void    *ev[CRP_RP_RING][CRP_RP_NEV];  /* ring of event sets: stats of an exec are folded in later,     */
     double  ring_host_t0[CRP_RP_RING];     /* when its events have completed, without stalling the host     */
     double  ring_host_t1[CRP_RP_RING];
+    void    *mark[CRP_RP_RING][CRP_RP_NEV]; /* event that closes each phase (a phase without work reuses the previous one) */
     int     ring_head, ring_count;
     double  t_h2d, t_d2h;       /* staging of host B / C (seconds, device time)                      */
     int     staged;             /* 1: exchange through pinned host memory + MPI (ranks share a GPU)  */

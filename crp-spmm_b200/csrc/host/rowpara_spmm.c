@@ -343,7 +343,7 @@ static void rp_collect(rp_spmm_p rp, const int wait)
     while (d->ring_count > 0)
     {
         const int k = (d->ring_head - d->ring_count + CRP_RP_RING) % CRP_RP_RING;      /* oldest */
-        void **ev = d->ev[k];
+        void **ev = d->mark[k];
         if (wait) crp_cuda_event_sync(ev[CRP_EV_END]);
         else if (!crp_cuda_event_done(ev[CRP_EV_END])) break;
         rp->t_pack += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_B_IN],   ev[CRP_EV_PACKED]);
@@ -417,6 +417,9 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     rp_collect(rp, d->ring_count == CRP_RP_RING);
     const double host_t0 = get_wtime_sec();
     void **ev = d->ev[d->ring_head];
+    void **mark = d->mark[d->ring_head];
+    /* an event is recorded only after a phase that did work: timing events are not free on the device */
+#define CRP_MARK(i, did_work) do { if ((did_work) || (i) == CRP_EV_START) { crp_cuda_event_record(ev[i], stream); mark[i] = ev[i]; } else mark[i] = mark[(i) - 1]; } while (0)
     const int n = rp->glb_n, m = rp->A_nrow, nB = d->nB;
     const size_t es = (size_t) elem_size;
     const size_t row_bytes = es * (size_t) n;
@@ -424,7 +427,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     const int B_on_dev = (nB > 0 && n > 0) ? crp_cuda_ptr_is_device(B) : 1;
     const int C_on_dev = (m > 0 && n > 0) ? crp_cuda_ptr_is_device(C) : 1;
 
-    crp_cuda_event_record(ev[CRP_EV_START], stream);
+    CRP_MARK(CRP_EV_START, 1);
 
     /* ---- B as a row-major device matrix Bd (leading dimension ldBd) ---- */
     const void *Bd = B;
@@ -459,7 +462,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
             ldBd = (size_t) n;
         }
     }
-    crp_cuda_event_record(ev[CRP_EV_B_IN], stream);
+    CRP_MARK(CRP_EV_B_IN, Bd != B);
 
     /* ---- pack the rows other ranks need ---- */
     if (d->n_send_rows > 0 && n > 0)
@@ -468,11 +471,11 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         crp_cuda_gather_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, d->d_sendbuf, n, stream);
     }
     if (d->n_recv_rows > 0 && n > 0) grow_dev(&d->d_recvbuf, &d->recvbuf_bytes, row_bytes * (size_t) d->n_recv_rows);
-    crp_cuda_event_record(ev[CRP_EV_PACKED], stream);
+    CRP_MARK(CRP_EV_PACKED, d->n_send_rows > 0 && n > 0);
 
     /* ---- exchange ---- */
     if (n > 0) rp_exchange(rp, d, row_bytes, stream);
-    crp_cuda_event_record(ev[CRP_EV_XCHG], stream);
+    CRP_MARK(CRP_EV_XCHG, rp->nproc > 1 && (d->n_send_rows > 0 || d->n_recv_rows > 0) && n > 0);
 
     /* ---- local product, reading own rows from Bd and remote rows from the receive buffer ---- */
     void *Cd = C;
@@ -488,7 +491,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         }
         crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
     }
-    crp_cuda_event_record(ev[CRP_EV_SPMM], stream);
+    CRP_MARK(CRP_EV_SPMM, m > 0 && n > 0);
 
     /* ---- C back to where the caller wants it ---- */
     if (m > 0 && n > 0 && !C_direct)
@@ -506,7 +509,8 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
             crp_cuda_memcpy2d_async(d->d_Lwork, es * (size_t) m, C, es * (size_t) ldC, es * (size_t) m, (size_t) n, stream);
         }
     }
-    crp_cuda_event_record(ev[CRP_EV_END], stream);
+    CRP_MARK(CRP_EV_END, m > 0 && n > 0 && !C_direct);
+#undef CRP_MARK
 
     const int k = d->ring_head;
     d->ring_head = (d->ring_head + 1) % CRP_RP_RING;
@@ -516,7 +520,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     rp->n_exec++;
     if (crp_opt_blocking() || !C_on_dev || !B_on_dev)
     {
-        crp_cuda_event_sync(ev[CRP_EV_END]);
+        crp_cuda_event_sync(mark[CRP_EV_END]);
         d->ring_host_t1[k] = get_wtime_sec();
         rp_collect(rp, 1);
     }
