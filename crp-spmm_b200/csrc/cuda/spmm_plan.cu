@@ -13,7 +13,7 @@ void crp_launch_rowsplit(
     T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
 );
 template <typename T, int VEC>
-void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s);
+void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
 
 extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int x0_rows, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint)
 {
@@ -81,12 +81,12 @@ static void spmm_dispatch(
     const int x0_rows = plan->x0_rows;
     const crp_rowgroup *rg = &plan->rg;
     const bool want_rg = (plan->variant == CRP_VARIANT_AUTO || plan->variant == CRP_VARIANT_ROWGROUP);
-    if (want_rg && rg->R > 1 && rg->ngroups > 0 && beta == (T) 0)
+    if (want_rg && rg->R > 1 && rg->ngroups > 0)
     {
         const uintptr_t ptrs = (uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C;
         const bool vec_ok = (n % VECN == 0) && (ldx0 % VECN == 0) && (X1 == NULL || ldx1 % VECN == 0) && (ldc % VECN == 0) && ((ptrs & 15) == 0);
-        if (vec_ok) crp_launch_rowgroup<T, VECN>(rg, bval, n / VECN, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s);
-        else        crp_launch_rowgroup<T, 1>(rg, bval, n, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s);
+        if (vec_ok) crp_launch_rowgroup<T, VECN>(rg, bval, n / VECN, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
+        else        crp_launch_rowgroup<T, 1>(rg, bval, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
         if (rg->nrest > 0)
             crp_launch_rowsplit<T, VECN>(plan, rg->nrest, rg->d_rest, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
         snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowgroup_%s_R%d%s", tname, rg->R, rg->nrest > 0 ? "+rowsplit" : "");

@@ -384,6 +384,234 @@ __global__ void __launch_bounds__(BS) spmm_rowgroup_kernel(
     }
 }
 
+// ---- variant with the block values and columns staged through shared memory ("sv") ----
+// In the kernel above every iteration waits for the block values: they stream from HBM (first
+// touch, no reuse), so each NB-block step pays a full DRAM round trip (~1400 cycles, ncu:
+// long_scoreboard 2.9 of 4.0 stall slots) before its FMAs.  Here a warp copies the values and
+// columns of the next CB blocks of its group into its private shared-memory ring with cp.async
+// (LDGSTS, no registers held) while it works on the current CB blocks, and reads them back with
+// broadcast LDS (29 cycles).  Only the B-row gathers remain long-latency loads.
+__device__ __forceinline__ void cp_async_bytes16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_bytes8(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_bytes4(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <typename T, int R>
+__device__ __forceinline__ void lds_block_vals(const T *p, T (&a)[R])
+{
+    constexpr int PER16 = 16 / (int) sizeof(T);
+    if constexpr ((R % PER16) == 0)
+    {
+        #pragma unroll
+        for (int i = 0; i < R / PER16; i++)
+        {
+            const typename vec128<T>::type t = reinterpret_cast<const typename vec128<T>::type *>(p)[i];
+            const T *tp = reinterpret_cast<const T *>(&t);
+            #pragma unroll
+            for (int e = 0; e < PER16; e++) a[i * PER16 + e] = tp[e];
+        }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < R; i++) a[i] = p[i];
+    }
+}
+
+template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE, int PF>
+__global__ void __launch_bounds__(BS) spmm_rowgroup_sv_kernel(
+    const int ngroups, const int *__restrict__ grow, const int *__restrict__ gptr,
+    const int *__restrict__ bcol, const T *__restrict__ bval,
+    const int nv,
+    const T *__restrict__ X0, const size_t ldx0, const int x0_rows,
+    const T *__restrict__ X1, const size_t ldx1,
+    const T alpha, const T beta, T *__restrict__ C, const size_t ldc
+)
+{
+    constexpr int WPB = BS / 32;
+    constexpr int VAL_BYTES = CB * R * (int) sizeof(T);
+    constexpr int GRAN = (R * (int) sizeof(T)) % 16 == 0 ? 16 : ((R * (int) sizeof(T)) % 8 == 0 ? 8 : 4);
+    __shared__ __align__(16) unsigned char s_val[WPB][2][VAL_BYTES];
+    __shared__ int s_col[WPB][2][CB];
+
+    const int wib  = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + wib;            // one group per warp
+    const int v0 = blockIdx.y * (32 * U);
+    if (g >= ngroups) return;                        // whole warp leaves together: no block-level barrier below
+    const int p_beg = __ldg(gptr + g), p_end = __ldg(gptr + g + 1), row0 = __ldg(grow + g);
+
+    int voff[U];
+    #pragma unroll
+    for (int u = 0; u < U; u++) { const int v = v0 + u * 32 + lane; voff[u] = (v < nv) ? v * VEC : -1; }
+
+    T acc[R][U][VEC];
+    #pragma unroll
+    for (int r = 0; r < R; r++)
+        #pragma unroll
+        for (int u = 0; u < U; u++)
+            #pragma unroll
+            for (int e = 0; e < VEC; e++) acc[r][u][e] = (T) 0;
+
+    // copy values and columns of blocks [pc, pc + nb) into ring slot `buf`
+    auto stage = [&](const int buf, const int pc, const int nb) {
+        const char *src = (const char *) (bval + (size_t) pc * R);
+        const int nbytes = nb * R * (int) sizeof(T);
+        for (int off = lane * GRAN; off < nbytes; off += 32 * GRAN)
+        {
+            if (GRAN == 16) cp_async_bytes16(&s_val[wib][buf][off], src + off);
+            else if (GRAN == 8) cp_async_bytes8(&s_val[wib][buf][off], src + off);
+            else cp_async_bytes4(&s_val[wib][buf][off], src + off);
+        }
+        for (int j = lane; j < nb; j += 32) cp_async_bytes4(&s_col[wib][buf][j], bcol + pc + j);
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    stage(0, p_beg, min(CB, p_end - p_beg));
+    for (int pc = p_beg; pc < p_end; pc += CB, buf ^= 1)
+    {
+        const int nb = min(CB, p_end - pc);
+        cp_async_wait_all();
+        __syncwarp();
+        if (pc + CB < p_end) stage(buf ^ 1, pc + CB, min(CB, p_end - pc - CB));
+        const T *sv = reinterpret_cast<const T *>(&s_val[wib][buf][0]);
+        const int *sc = &s_col[wib][buf][0];
+        int j = 0;
+        auto row_of = [&](const int jj) -> const T * {
+            const int c = sc[jj];
+            return (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
+        };
+        auto load_x = [&](const int jj, T (&x)[NB][U][VEC]) {
+            #pragma unroll
+            for (int q = 0; q < NB; q++)
+            {
+                const T *xr = row_of(jj + q);
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                {
+                    if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], x[q][u]);
+                    else { for (int e = 0; e < VEC; e++) x[q][u][e] = (T) 0; }
+                }
+            }
+        };
+        auto fma_x = [&](const int jj, const T (&x)[NB][U][VEC]) {
+            #pragma unroll
+            for (int q = 0; q < NB; q++)
+            {
+                T a[R];
+                lds_block_vals<T, R>(sv + (size_t) (jj + q) * R, a);
+                #pragma unroll
+                for (int r = 0; r < R; r++)
+                    #pragma unroll
+                    for (int u = 0; u < U; u++)
+                        #pragma unroll
+                        for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], x[q][u][e], acc[r][u][e]);
+            }
+        };
+        // L1 prefetch of the B rows PF blocks ahead (lane l covers the l-th 128-byte line of the column chunk)
+        constexpr int CHUNK_BYTES = 32 * U * VEC * (int) sizeof(T);
+        const bool pf_lane = (PF > 0) && (lane * 128 < CHUNK_BYTES) && (v0 * VEC + lane * (128 / (int) sizeof(T)) < nv * VEC);
+        auto prefetch = [&](const int jj) {
+            if (PF > 0 && jj < nb && pf_lane)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"((const char *) row_of(jj) + (size_t) v0 * VEC * sizeof(T) + lane * 128));
+        };
+        if (PF > 0) { for (int d = 0; d < PF; d++) prefetch(d); }
+        if (PIPE == 0)
+        {
+            for (; j + NB <= nb; j += NB)
+            {
+                T x[NB][U][VEC];
+                #pragma unroll
+                for (int q = 0; q < NB; q++) prefetch(j + PF + q);
+                load_x(j, x);
+                fma_x(j, x);
+            }
+        } else {
+            T xa[NB][U][VEC], xb[NB][U][VEC];
+            if (j + NB <= nb) load_x(j, xa);
+            while (j + NB <= nb)
+            {
+                const bool nb1 = (j + 2 * NB <= nb);
+                if (nb1) load_x(j + NB, xb);
+                fma_x(j, xa);
+                j += NB;
+                if (!nb1) break;
+                const bool nb2 = (j + 2 * NB <= nb);
+                if (nb2) load_x(j + NB, xa);
+                fma_x(j, xb);
+                j += NB;
+                if (!nb2) break;
+            }
+        }
+        for (; j < nb; j++)
+        {
+            const int c = sc[j];
+            const T *xr = (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
+            T a[R];
+            lds_block_vals<T, R>(sv + (size_t) j * R, a);
+            #pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (voff[u] < 0) continue;
+                T x[VEC];
+                xload<T, VEC>::ld(xr + voff[u], x);
+                #pragma unroll
+                for (int r = 0; r < R; r++)
+                    #pragma unroll
+                    for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], x[e], acc[r][u][e]);
+            }
+        }
+        __syncwarp();       // everybody is done with slot `buf` before it is refilled two chunks later
+    }
+
+    #pragma unroll
+    for (int r = 0; r < R; r++)
+    {
+        T *crow = C + (size_t) (row0 + r) * ldc;
+        #pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            if (voff[u] < 0) continue;
+            T out[VEC];
+            if (beta == (T) 0)
+            {
+                #pragma unroll
+                for (int e = 0; e < VEC; e++) out[e] = alpha * acc[r][u][e];
+            } else {
+                T old[VEC];
+                #pragma unroll
+                for (int e = 0; e < VEC; e++) old[e] = crow[voff[u] + e];
+                #pragma unroll
+                for (int e = 0; e < VEC; e++) out[e] = fma(alpha, acc[r][u][e], beta * old[e]);
+            }
+            xload<T, VEC>::st(crow + voff[u], out);
+        }
+    }
+}
+
+template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE = 0, int PF = 0>
+static void rg_launch_sv(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s)
+{
+    const unsigned blocks = (unsigned) ((rg->ngroups + BS / 32 - 1) / (BS / 32));
+    const unsigned chunks = (unsigned) ((nv + 32 * U - 1) / (32 * U));
+    if (blocks == 0) return;
+    spmm_rowgroup_sv_kernel<T, VEC, R, U, NB, BS, CB, PIPE, PF><<<dim3(blocks, chunks), BS, 0, s>>>(
+        rg->ngroups, rg->d_grow, rg->d_gptr, rg->d_bcol, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc);
+    CRP_LAUNCH_CHECK();
+}
+
 template <typename T, int VEC, int R, int LPR, int U, int NB = 2, int PIPE = 0, int PF = 0, int BS = 256>
 static void rg_launch_one(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
 {
@@ -422,6 +650,30 @@ static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, 
             case 11: CRP_RGX(1, 4, 0, 16, 256);
             case 12: CRP_RGX(4, 1, 0, 8, 128);
             case 13: CRP_RGX(2, 1, 1, 0, 256);
+#define CRP_RGSV(U, NB, BS, CB) rg_launch_sv<T, VEC, R, U, NB, BS, CB>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, (T) 0, C, ldc, s); return true
+            case 20: CRP_RGSV(4, 2, 128, 32);
+            case 21: CRP_RGSV(4, 2, 256, 32);
+            case 22: CRP_RGSV(4, 1, 128, 32);
+            case 23: CRP_RGSV(4, 4, 128, 32);
+            case 24: CRP_RGSV(2, 2, 128, 32);
+            case 25: CRP_RGSV(2, 4, 128, 32);
+            case 26: CRP_RGSV(2, 4, 256, 32);
+            case 27: CRP_RGSV(4, 2, 128, 64);
+            case 28: CRP_RGSV(4, 3, 128, 32);
+            case 29: CRP_RGSV(1, 4, 256, 32);
+#define CRP_RGSV2(U, NB, BS, CB, PIPE, PF) rg_launch_sv<T, VEC, R, U, NB, BS, CB, PIPE, PF>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, (T) 0, C, ldc, s); return true
+            case 30: CRP_RGSV2(4, 1, 128, 32, 1, 0);
+            case 31: CRP_RGSV2(4, 2, 128, 32, 1, 0);
+            case 32: CRP_RGSV2(2, 2, 128, 32, 1, 0);
+            case 33: CRP_RGSV2(4, 2, 128, 32, 0, 4);
+            case 34: CRP_RGSV2(4, 2, 128, 32, 0, 8);
+            case 35: CRP_RGSV2(2, 2, 128, 32, 0, 8);
+            case 36: CRP_RGSV2(4, 1, 128, 32, 0, 8);
+            case 37: CRP_RGSV2(2, 1, 128, 32, 1, 0);
+            case 38: CRP_RGSV2(4, 2, 64, 32, 0, 0);
+            case 39: CRP_RGSV2(4, 2, 96, 32, 0, 0);
+#undef CRP_RGSV2
+#undef CRP_RGSV
             default: return false;
         }
 #undef CRP_RGX
@@ -430,25 +682,28 @@ static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, 
 }
 
 template <typename T, int VEC, int R>
-static void rg_launch_R(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
+static void rg_launch_R(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s)
 {
-    if (rg_launch_experiment<T, VEC, R>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)) return;
+    if (beta == (T) 0 && rg_launch_experiment<T, VEC, R>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)) return;
     constexpr int UMAX = (R * VEC * (int) sizeof(T) <= 6 * 16) ? 4 : 2;       // keep the accumulator tile <= 96 registers
+    // Full-warp groups: values / columns staged through shared memory (measured on the pwtk-shaped
+    // n = 256 fp64 case: 0.60 -> 0.42 ms); 128-thread CTAs so that 168 registers still give 12 warps per SM.
+#define CRP_SV(U, NB, BS) rg_launch_sv<T, VEC, R, U, NB, BS, 32>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s)
 #define CRP_RG(LPR, U) rg_launch_one<T, VEC, R, LPR, U>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)
-    // 128-thread CTAs for the widest tile: 168 registers per thread -> 3 CTAs (12 warps) per SM instead of 8 warps (measured 0.72 -> 0.60 ms)
-    if (nv >= 128 && UMAX >= 4) rg_launch_one<T, VEC, R, 32, 4, 2, 0, 0, 128>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s);
-    else if (nv >= 64)          CRP_RG(32, 2);
-    else if (nv > 16)           CRP_RG(32, 1);
+    if (nv >= 128 && UMAX >= 4) CRP_SV(4, 2, 128);
+    else if (nv >= 64)          CRP_SV(2, 2, 128);
+    else if (nv > 16 || beta != (T) 0) CRP_SV(1, 4, 256);
     else if (nv > 8)            CRP_RG(16, 1);
     else if (nv > 4)            CRP_RG(8, 1);
     else                        CRP_RG(4, 1);
 #undef CRP_RG
+#undef CRP_SV
 }
 
 template <typename T, int VEC>
-void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
+void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s)
 {
-#define CRP_RGR(R) rg_launch_R<T, VEC, R>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)
+#define CRP_RGR(R) rg_launch_R<T, VEC, R>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s)
     switch (rg->R)
     {
         case 2: CRP_RGR(2); break;
@@ -461,7 +716,7 @@ void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T 
 #undef CRP_RGR
 }
 
-template void crp_launch_rowgroup<double, 2>(const crp_rowgroup *, const double *, int, const double *, size_t, int, const double *, size_t, double, double *, size_t, cudaStream_t);
-template void crp_launch_rowgroup<double, 1>(const crp_rowgroup *, const double *, int, const double *, size_t, int, const double *, size_t, double, double *, size_t, cudaStream_t);
-template void crp_launch_rowgroup<float, 4>(const crp_rowgroup *, const float *, int, const float *, size_t, int, const float *, size_t, float, float *, size_t, cudaStream_t);
-template void crp_launch_rowgroup<float, 1>(const crp_rowgroup *, const float *, int, const float *, size_t, int, const float *, size_t, float, float *, size_t, cudaStream_t);
+template void crp_launch_rowgroup<double, 2>(const crp_rowgroup *, const double *, int, const double *, size_t, int, const double *, size_t, double, double, double *, size_t, cudaStream_t);
+template void crp_launch_rowgroup<double, 1>(const crp_rowgroup *, const double *, int, const double *, size_t, int, const double *, size_t, double, double, double *, size_t, cudaStream_t);
+template void crp_launch_rowgroup<float, 4>(const crp_rowgroup *, const float *, int, const float *, size_t, int, const float *, size_t, float, float, float *, size_t, cudaStream_t);
+template void crp_launch_rowgroup<float, 1>(const crp_rowgroup *, const float *, int, const float *, size_t, int, const float *, size_t, float, float, float *, size_t, cudaStream_t);

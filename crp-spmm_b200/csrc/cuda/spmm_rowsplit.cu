@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(256) spmm_rowsplit_kernel(
             }
         }
 
-        if (ridx < m)
+        // beta == 1 and no nonzeros: C row unchanged, do not touch it (the received-rows pass of the overlap mode)
+        if (ridx < m && !(p_beg == p_end && beta == (T) 1))
         {
             T *crow = C + (size_t) row * ldc;
             #pragma unroll

@@ -45,12 +45,17 @@ void  crp_nccl_shutdown(void);
 int  *crp_comm_ranks_in_parent(MPI_Comm sub, MPI_Comm parent);
 
 /* ---- device-side state of a row-parallel engine (rowpara_spmm.c) ---- */
-enum { CRP_EV_START = 0, CRP_EV_B_IN, CRP_EV_PACKED, CRP_EV_XCHG, CRP_EV_SPMM, CRP_EV_END, CRP_RP_NEV };
+enum { CRP_EV_START = 0, CRP_EV_B_IN, CRP_EV_PACKED, CRP_EV_XCHG, CRP_EV_DIAG, CRP_EV_OFF0, CRP_EV_SPMM, CRP_EV_END, CRP_RP_NEV };
 enum { CRP_RP_RING = 8 };
 
 struct crp_rp_dev
 {
-    crp_spmm_plan *plan;        /* device CSR with "virtual" column ids (see rp_build_device_state) */
+    crp_spmm_plan *plan;        /* device CSR with "virtual" column ids (see rp_build_device_state);
+                                 * in overlap mode only the entries that reference this rank's own B rows */
+    crp_spmm_plan *plan_off;    /* overlap mode: the entries that reference received rows (NULL if none) */
+    int     overlap;            /* 1: pack + exchange run on stream2 concurrently with the own-rows product */
+    void    *stream2;           /* communication stream of the overlap mode                          */
+    int     ring_overlap[CRP_RP_RING];
     int     nB;                 /* B rows owned by this rank                                         */
     int     n_send_rows;        /* rows packed per exec                                              */
     int     n_recv_rows;        /* remote rows received per exec                                     */

@@ -224,7 +224,38 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
         ASSERT_PRINTF(vcol[i] >= 0, "rp_spmm: column %d of the local A has no source row\n", rp->A_colidx[i]);
     }
     free(vid);
-    d->plan = crp_cuda_spmm_plan_create(rp->A_nrow, d->nB + d->n_recv_rows, d->nB, rp->A_rowptr, vcol, rp->A_val, n);
+
+    /* Overlap mode (default with NCCL): the product is split by column into the part that needs only
+     * this rank's own B rows - it runs while the exchange is in flight - and the part that needs
+     * received rows, accumulated afterwards (C += ...).  Rows of A stay whole in each part's CSR. */
+    int want_overlap;
+    GET_ENV_INT_VAR(want_overlap, "CRP_SPMM_OVERLAP", "overlap", 1, 0, 1, 0);
+    d->overlap = (want_overlap && nproc > 1 && !d->staged && (d->n_send_rows > 0 || d->n_recv_rows > 0)) ? 1 : 0;
+    if (d->overlap && d->n_recv_rows > 0)
+    {
+        const int m = rp->A_nrow;
+        int *rp_d = (int *) xmalloc(sizeof(int) * ((size_t) m + 1)), *rp_o = (int *) xmalloc(sizeof(int) * ((size_t) m + 1));
+        int *ci_d = (int *) xmalloc(sizeof(int) * (size_t) (nnz > 0 ? nnz : 1)), *ci_o = (int *) xmalloc(sizeof(int) * (size_t) (nnz > 0 ? nnz : 1));
+        double *v_d = (double *) xmalloc(sizeof(double) * (size_t) (nnz > 0 ? nnz : 1)), *v_o = (double *) xmalloc(sizeof(double) * (size_t) (nnz > 0 ? nnz : 1));
+        int nd = 0, no = 0;
+        rp_d[0] = rp_o[0] = 0;
+        for (int i = 0; i < m; i++)
+        {
+            for (int p = rp->A_rowptr[i]; p < rp->A_rowptr[i + 1]; p++)
+            {
+                if (vcol[p] < d->nB) { ci_d[nd] = vcol[p]; v_d[nd++] = rp->A_val[p]; }
+                else                 { ci_o[no] = vcol[p]; v_o[no++] = rp->A_val[p]; }
+            }
+            rp_d[i + 1] = nd;
+            rp_o[i + 1] = no;
+        }
+        d->plan = crp_cuda_spmm_plan_create(m, d->nB + d->n_recv_rows, d->nB, rp_d, ci_d, v_d, n);
+        d->plan_off = (no > 0) ? crp_cuda_spmm_plan_create(m, d->nB + d->n_recv_rows, d->nB, rp_o, ci_o, v_o, n) : NULL;
+        free(rp_d); free(rp_o); free(ci_d); free(ci_o); free(v_d); free(v_o);
+    } else {
+        d->plan = crp_cuda_spmm_plan_create(rp->A_nrow, d->nB + d->n_recv_rows, d->nB, rp->A_rowptr, vcol, rp->A_val, n);
+        d->plan_off = NULL;
+    }
     free(vcol);
 
     if (d->n_send_rows > 0)
@@ -233,16 +264,10 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
         crp_cuda_memcpy_h2d(rp->rB_sridxs, d->d_sridxs, sizeof(int) * (size_t) d->n_send_rows);
     }
     d->stream = crp_cuda_stream_create();
+    d->stream2 = crp_cuda_stream_create();
     for (int k = 0; k < CRP_RP_RING; k++)
         for (int i = 0; i < CRP_RP_NEV; i++) d->ev[k][i] = crp_cuda_event_create();
 
-    /* transport: NCCL needs one device per rank */
-    int wsize = 1;
-    MPI_Comm_size(MPI_COMM_WORLD, &wsize);
-    int transport;
-    GET_ENV_INT_VAR(transport, "CRP_SPMM_TRANSPORT", "transport", -1, 0, 1, 0);   /* 0 NCCL, 1 staged MPI */
-    if (transport < 0) transport = (wsize > crp_cuda_device_count()) ? 1 : 0;
-    d->staged = transport;
     d->nc = NULL;
     d->peer_nc_rank = NULL;
     if (nproc > 1 && !d->staged)
@@ -257,7 +282,9 @@ static void rp_free_device_state(rp_spmm_p rp)
     struct crp_rp_dev *d = (struct crp_rp_dev *) rp->dev;
     if (d == NULL) return;
     crp_cuda_stream_sync(d->stream);
+    crp_cuda_stream_sync(d->stream2);
     crp_cuda_spmm_plan_destroy(d->plan);
+    crp_cuda_spmm_plan_destroy(d->plan_off);
     crp_cuda_free_dev(d->d_sridxs);
     crp_cuda_free_dev(d->d_sendbuf);
     crp_cuda_free_dev(d->d_recvbuf);
@@ -269,6 +296,7 @@ static void rp_free_device_state(rp_spmm_p rp)
     for (int k = 0; k < CRP_RP_RING; k++)
         for (int i = 0; i < CRP_RP_NEV; i++) crp_cuda_event_destroy(d->ev[k][i]);
     crp_cuda_stream_destroy(d->stream);
+    crp_cuda_stream_destroy(d->stream2);
     free(d->send_rows);
     free(d->recv_rows);
     free(d->peer_nc_rank);
@@ -348,7 +376,10 @@ static void rp_collect(rp_spmm_p rp, const int wait)
         else if (!crp_cuda_event_done(ev[CRP_EV_END])) break;
         rp->t_pack += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_B_IN],   ev[CRP_EV_PACKED]);
         rp->t_a2a  += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_PACKED], ev[CRP_EV_XCHG]);
-        rp->t_spmm += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_XCHG],   ev[CRP_EV_SPMM]);
+        if (d->ring_overlap[k])     /* own-rows product (concurrent with the exchange) + received-rows product */
+            rp->t_spmm += 1e-3 * (crp_cuda_event_elapsed_ms(ev[CRP_EV_B_IN], ev[CRP_EV_DIAG]) + crp_cuda_event_elapsed_ms(ev[CRP_EV_OFF0], ev[CRP_EV_SPMM]));
+        else
+            rp->t_spmm += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_XCHG], ev[CRP_EV_SPMM]);
         d->t_h2d   += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_START],  ev[CRP_EV_B_IN]);
         d->t_d2h   += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_SPMM],   ev[CRP_EV_END]);
         /* blocking execs: host wall clock of the call; enqueue-only execs: device time start -> end */
@@ -419,7 +450,8 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     void **ev = d->ev[d->ring_head];
     void **mark = d->mark[d->ring_head];
     /* an event is recorded only after a phase that did work: timing events are not free on the device */
-#define CRP_MARK(i, did_work) do { if ((did_work) || (i) == CRP_EV_START) { crp_cuda_event_record(ev[i], stream); mark[i] = ev[i]; } else mark[i] = mark[(i) - 1]; } while (0)
+#define CRP_MARK_ON(i, did_work, st) do { if ((did_work) || (i) == CRP_EV_START) { crp_cuda_event_record(ev[i], st); mark[i] = ev[i]; } else mark[i] = mark[(i) - 1]; } while (0)
+#define CRP_MARK(i, did_work) CRP_MARK_ON(i, did_work, stream)
     const int n = rp->glb_n, m = rp->A_nrow, nB = d->nB;
     const size_t es = (size_t) elem_size;
     const size_t row_bytes = es * (size_t) n;
@@ -464,34 +496,48 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     }
     CRP_MARK(CRP_EV_B_IN, Bd != B);
 
-    /* ---- pack the rows other ranks need ---- */
+    /* ---- pack the rows other ranks need, exchange: on the communication stream in overlap mode ---- */
+    const int overlap = d->overlap;
+    void *cs = overlap ? d->stream2 : stream;
+    if (overlap)
+    {
+        CRP_MARK(CRP_EV_B_IN, 1);                               /* fork point: B is in place */
+        crp_cuda_stream_wait_event(cs, mark[CRP_EV_B_IN]);
+    }
     if (d->n_send_rows > 0 && n > 0)
     {
         grow_dev(&d->d_sendbuf, &d->sendbuf_bytes, row_bytes * (size_t) d->n_send_rows);
-        crp_cuda_gather_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, d->d_sendbuf, n, stream);
+        crp_cuda_gather_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, d->d_sendbuf, n, cs);
     }
     if (d->n_recv_rows > 0 && n > 0) grow_dev(&d->d_recvbuf, &d->recvbuf_bytes, row_bytes * (size_t) d->n_recv_rows);
-    CRP_MARK(CRP_EV_PACKED, d->n_send_rows > 0 && n > 0);
-
-    /* ---- exchange ---- */
-    if (n > 0) rp_exchange(rp, d, row_bytes, stream);
-    CRP_MARK(CRP_EV_XCHG, rp->nproc > 1 && (d->n_send_rows > 0 || d->n_recv_rows > 0) && n > 0);
+    CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0 && n > 0, cs);
+    if (n > 0) rp_exchange(rp, d, row_bytes, cs);
+    CRP_MARK_ON(CRP_EV_XCHG, overlap || (rp->nproc > 1 && (d->n_send_rows > 0 || d->n_recv_rows > 0) && n > 0), cs);
 
     /* ---- local product, reading own rows from Bd and remote rows from the receive buffer ---- */
     void *Cd = C;
     size_t ldCd = (size_t) ldC;
     const int C_direct = (BC_layout == 0) && C_on_dev;
-    if (m > 0 && n > 0)
+    if (m > 0 && n > 0 && !C_direct)
     {
-        if (!C_direct)
-        {
-            grow_dev(&d->d_Cwork, &d->Cwork_bytes, row_bytes * (size_t) m);
-            Cd = d->d_Cwork;
-            ldCd = (size_t) n;
-        }
-        crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
+        grow_dev(&d->d_Cwork, &d->Cwork_bytes, row_bytes * (size_t) m);
+        Cd = d->d_Cwork;
+        ldCd = (size_t) n;
     }
-    CRP_MARK(CRP_EV_SPMM, m > 0 && n > 0);
+    if (!overlap)
+    {
+        mark[CRP_EV_DIAG] = mark[CRP_EV_OFF0] = mark[CRP_EV_XCHG];
+        if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
+        CRP_MARK(CRP_EV_SPMM, m > 0 && n > 0);
+    } else {
+        if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
+        CRP_MARK(CRP_EV_DIAG, 1);
+        crp_cuda_stream_wait_event(stream, mark[CRP_EV_XCHG]);  /* join: received rows are in place, sends are done */
+        CRP_MARK(CRP_EV_OFF0, 1);
+        if (m > 0 && n > 0 && d->plan_off != NULL)
+            crp_cuda_spmm_exec(d->plan_off, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 1.0, Cd, (int) ldCd, stream);
+        CRP_MARK(CRP_EV_SPMM, 1);
+    }
 
     /* ---- C back to where the caller wants it ---- */
     if (m > 0 && n > 0 && !C_direct)
@@ -511,11 +557,13 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     }
     CRP_MARK(CRP_EV_END, m > 0 && n > 0 && !C_direct);
 #undef CRP_MARK
+#undef CRP_MARK_ON
 
     const int k = d->ring_head;
     d->ring_head = (d->ring_head + 1) % CRP_RP_RING;
     d->ring_count++;
     d->ring_host_t0[k] = host_t0;
+    d->ring_overlap[k] = overlap;
     d->ring_host_t1[k] = 0.0;
     rp->n_exec++;
     if (crp_opt_blocking() || !C_on_dev || !B_on_dev)
