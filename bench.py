@@ -69,7 +69,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -221,8 +221,11 @@ def main():
     t1 = time.time()
     launches = L.crp_kernel_launch_count() - launches0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    my_ms = sum(L.crp_cuda_event_elapsed_ms(s, e) for s, e in ev) / a.steps
+    step_ms = [L.crp_cuda_event_elapsed_ms(s, e) for s, e in ev]
+    my_ms = sum(step_ms) / a.steps
     ms_per_step = capi.mpi_allreduce_max(my_ms)
+    ms_median = capi.mpi_allreduce_max(float(np.median(step_ms)))
+    host_ms_per_step = 1e3 * (t1 - t0) / a.steps
     value = flops_total / (ms_per_step * 1e-3) / 1e9
 
     # roofline of the local-SpMM kernel, from the engine's own CUDA events around it (same timed region)
@@ -291,7 +294,9 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_s, "data": "synthetic",
             "config": {"workload": desc, "n": n, "nnz": nnz, "grid": f"{pb.pm}x{pb.pn}", "comm_cost": pb.comm_cost,
                        "l2": "256 MiB memset between timed steps (outside the event pairs); B + C + A = %.0f MB per job" % (bytes_sum / 1e6),
-                       "kernel": kern, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow", "checksum": csum},
+                       "kernel": kern, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow", "checksum": csum,
+                       "ms_per_step_median": ms_median, "host_wall_ms_per_step_incl_flush": host_ms_per_step,
+                       "overlap": int(os.environ.get("CRP_SPMM_OVERLAP", "1")) if nproc > 1 else 0},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ach if nproc == 1 else ach_job, "peak": peak, "unit": "GB/s",
                          "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": None, "peak_source": peak_src, "kernel": kern,

@@ -167,6 +167,15 @@ extern "C" void *crp_cuda_stream_create(void)
     return (void *) s;
 }
 
+extern "C" void *crp_cuda_stream_create_high_priority(void)
+{
+    int lo = 0, hi = 0;
+    CRP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s;
+    CRP_CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+    return (void *) s;
+}
+
 extern "C" void crp_cuda_stream_destroy(void *stream) { if (stream) CRP_CUDA_CHECK(cudaStreamDestroy(as_stream(stream))); }
 
 extern "C" void *crp_cuda_event_create(void)

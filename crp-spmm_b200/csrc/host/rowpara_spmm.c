@@ -225,6 +225,14 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     }
     free(vid);
 
+    /* transport: NCCL needs one device per rank; ranks that share a GPU stage the exchange through the host */
+    int wsize = 1;
+    MPI_Comm_size(MPI_COMM_WORLD, &wsize);
+    int transport;
+    GET_ENV_INT_VAR(transport, "CRP_SPMM_TRANSPORT", "transport", -1, 0, 1, 0);   /* 0 NCCL, 1 staged MPI */
+    if (transport < 0) transport = (wsize > crp_cuda_device_count()) ? 1 : 0;
+    d->staged = transport;
+
     /* Overlap mode (default with NCCL): the product is split by column into the part that needs only
      * this rank's own B rows - it runs while the exchange is in flight - and the part that needs
      * received rows, accumulated afterwards (C += ...).  Rows of A stay whole in each part's CSR. */
@@ -264,7 +272,7 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
         crp_cuda_memcpy_h2d(rp->rB_sridxs, d->d_sridxs, sizeof(int) * (size_t) d->n_send_rows);
     }
     d->stream = crp_cuda_stream_create();
-    d->stream2 = crp_cuda_stream_create();
+    d->stream2 = crp_cuda_stream_create_high_priority();
     for (int k = 0; k < CRP_RP_RING; k++)
         for (int i = 0; i < CRP_RP_NEV; i++) d->ev[k][i] = crp_cuda_event_create();
 

@@ -159,6 +159,7 @@ def load():
     L.crp_cuda_memcpy_d2d.argtypes = [vp, vp, sz]
     L.crp_cuda_memcpy_async.argtypes = [vp, vp, sz, vp]
     L.crp_cuda_stream_create.restype = vp
+    L.crp_cuda_stream_create_high_priority.restype = vp
     L.crp_cuda_stream_destroy.argtypes = [vp]
     L.crp_cuda_stream_sync.argtypes = [vp]
     L.crp_cuda_event_create.restype = vp

@@ -60,6 +60,7 @@ void crp_cuda_host_unregister(const void *hptr);
 void  crp_cuda_device_sync(void);
 void  crp_cuda_stream_sync(void *stream);
 void *crp_cuda_stream_create(void);               /* non-blocking stream */
+void *crp_cuda_stream_create_high_priority(void); /* non-blocking, highest priority: its CTAs are placed first */
 void  crp_cuda_stream_destroy(void *stream);
 void *crp_cuda_event_create(void);
 void  crp_cuda_event_destroy(void *event);
