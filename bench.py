@@ -296,7 +296,7 @@ def main():
                        "l2": "256 MiB memset between timed steps (outside the event pairs); B + C + A = %.0f MB per job" % (bytes_sum / 1e6),
                        "kernel": kern, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow", "checksum": csum,
                        "ms_per_step_median": ms_median, "host_wall_ms_per_step_incl_flush": host_ms_per_step,
-                       "overlap": int(os.environ.get("CRP_SPMM_OVERLAP", "1")) if nproc > 1 else 0},
+                       "overlap": os.environ.get("CRP_SPMM_OVERLAP", "auto") if nproc > 1 else "n/a"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ach if nproc == 1 else ach_job, "peak": peak, "unit": "GB/s",
                          "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": None, "peak_source": peak_src, "kernel": kern,

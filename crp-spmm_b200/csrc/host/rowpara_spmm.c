@@ -236,8 +236,12 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     /* Overlap mode (default with NCCL): the product is split by column into the part that needs only
      * this rank's own B rows - it runs while the exchange is in flight - and the part that needs
      * received rows, accumulated afterwards (C += ...).  Rows of A stay whole in each part's CSR. */
+    /* Default: only when the exchange is big enough to be worth hiding.  Measured on 8 B200s: with
+     * 1.7 MB received per rank (pwtk-shaped, n = 256) the exchange is latency / skew bound and the split
+     * costs more than it hides (0.213 vs 0.204 ms per exec), so the threshold is a few MB. */
     int want_overlap;
-    GET_ENV_INT_VAR(want_overlap, "CRP_SPMM_OVERLAP", "overlap", 1, 0, 1, 0);
+    GET_ENV_INT_VAR(want_overlap, "CRP_SPMM_OVERLAP", "overlap", -1, 0, 1, 0);
+    if (want_overlap < 0) want_overlap = ((size_t) d->n_recv_rows * (size_t) n * sizeof(double) >= ((size_t) 4 << 20)) ? 1 : 0;
     d->overlap = (want_overlap && nproc > 1 && !d->staged && (d->n_send_rows > 0 || d->n_recv_rows > 0)) ? 1 : 0;
     if (d->overlap && d->n_recv_rows > 0)
     {
