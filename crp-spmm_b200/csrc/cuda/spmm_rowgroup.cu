@@ -478,9 +478,96 @@ __global__ void __launch_bounds__(BS) spmm_rowgroup_sv_kernel(
         cp_async_commit();
     };
 
+    if constexpr (PIPE == 2)
+    {
+        // Rolling prefetch: the registers of an (block, column-group) slot are reloaded with the data of the
+        // same slot NB blocks ahead right after the FMAs that consumed them, so the gathers of the next step
+        // are in flight during the whole FMA phase of the current one - without a second set of registers.
+        static_assert(CB % NB == 0, "chunk size must be a multiple of the blocks per step");
+        const int total = p_end - p_beg;
+        const int nchunk = (total + CB - 1) / CB;
+        stage(0, p_beg, min(CB, total));
+        cp_async_wait_all();
+        __syncwarp();
+        if (nchunk > 1) stage(1, p_beg + CB, min(CB, total - CB));
+        auto col_at = [&](const int jj) -> int { return s_col[wib][(jj / CB) & 1][jj % CB]; };
+        auto row_at = [&](const int jj) -> const T * {
+            const int c = col_at(jj);
+            return (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
+        };
+        T x[NB][U][VEC];
+        const int nfull = total - total % NB;
+        if (nfull > 0)
+        {
+            #pragma unroll
+            for (int q = 0; q < NB; q++)
+            {
+                const T *xr = row_at(q);
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                {
+                    if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], x[q][u]);
+                    else { for (int e = 0; e < VEC; e++) x[q][u][e] = (T) 0; }
+                }
+            }
+        }
+        for (int j = 0; j < nfull; j += NB)
+        {
+            const int chunk = j / CB;
+            const bool last_of_chunk = ((j % CB) == CB - NB);
+            if (last_of_chunk && chunk + 1 < nchunk) { cp_async_wait_all(); __syncwarp(); }     // next chunk readable for the look-ahead
+            const T *sv = reinterpret_cast<const T *>(&s_val[wib][chunk & 1][0]);
+            #pragma unroll
+            for (int q = 0; q < NB; q++)
+            {
+                T a[R];
+                lds_block_vals<T, R>(sv + (size_t) ((j % CB) + q) * R, a);
+                const int jn = j + NB + q;                  // the block that takes this slot next
+                const T *xn = row_at(jn < nfull ? jn : nfull - 1);
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                {
+                    #pragma unroll
+                    for (int r = 0; r < R; r++)
+                        #pragma unroll
+                        for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], x[q][u][e], acc[r][u][e]);
+                    if (voff[u] >= 0) xload<T, VEC>::ld(xn + voff[u], x[q][u]);
+                }
+            }
+            if (last_of_chunk)
+            {
+                __syncwarp();                               // everybody is done with this chunk's buffer
+                if (chunk + 2 < nchunk) stage(chunk & 1, p_beg + (chunk + 2) * CB, min(CB, total - (chunk + 2) * CB));
+            }
+        }
+        if (nfull < total)                                  // fewer than NB blocks left
+        {
+            const int chunk = nfull / CB;
+            if (nfull > 0 && (nfull % CB) == 0) { cp_async_wait_all(); __syncwarp(); }
+            const T *sv = reinterpret_cast<const T *>(&s_val[wib][chunk & 1][0]);
+            for (int j = nfull; j < total; j++)
+            {
+                const T *xr = row_at(j);
+                T a[R];
+                lds_block_vals<T, R>(sv + (size_t) (j % CB) * R, a);
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                {
+                    if (voff[u] < 0) continue;
+                    T xx[VEC];
+                    xload<T, VEC>::ld(xr + voff[u], xx);
+                    #pragma unroll
+                    for (int r = 0; r < R; r++)
+                        #pragma unroll
+                        for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], xx[e], acc[r][u][e]);
+                }
+            }
+        }
+    }
+
     int buf = 0;
-    stage(0, p_beg, min(CB, p_end - p_beg));
-    for (int pc = p_beg; pc < p_end; pc += CB, buf ^= 1)
+    if (PIPE != 2) stage(0, p_beg, min(CB, p_end - p_beg));
+    for (int pc = p_beg; PIPE != 2 && pc < p_end; pc += CB, buf ^= 1)
     {
         const int nb = min(CB, p_end - pc);
         cp_async_wait_all();
@@ -672,6 +759,12 @@ static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, 
             case 37: CRP_RGSV2(2, 1, 128, 32, 1, 0);
             case 38: CRP_RGSV2(4, 2, 64, 32, 0, 0);
             case 39: CRP_RGSV2(4, 2, 96, 32, 0, 0);
+            case 40: CRP_RGSV2(4, 2, 128, 32, 2, 0);
+            case 41: CRP_RGSV2(4, 1, 128, 32, 2, 0);
+            case 42: CRP_RGSV2(2, 2, 128, 32, 2, 0);
+            case 43: CRP_RGSV2(2, 4, 128, 32, 2, 0);
+            case 44: CRP_RGSV2(4, 4, 128, 32, 2, 0);
+            case 45: CRP_RGSV2(2, 2, 256, 32, 2, 0);
 #undef CRP_RGSV2
 #undef CRP_RGSV
             default: return false;

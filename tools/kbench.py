@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--f32", action="store_true")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--ldb0", action="store_true", help="experiment: leading dimension 0, every B row aliases row 0 (all gathers hit L1)")
     a = ap.parse_args()
     L = capi.load()
     gname, gkw, n, dts, mode, desc = bench.WORKLOADS[a.workload]
@@ -51,7 +52,7 @@ def main():
         for it in range(a.iters + 2):
             L.crp_cuda_memset_async(dF.p, it, 256 << 20, stream)
             L.crp_cuda_event_record(e0, stream)
-            L.crp_cuda_spmm_exec(plan, n, es, 1.0, dB.p, n, None, 0, 0.0, dC.p, n, stream)
+            L.crp_cuda_spmm_exec(plan, n, es, 1.0, dB.p, 0 if a.ldb0 else n, None, 0, 0.0, dC.p, n, stream)
             L.crp_cuda_event_record(e1, stream)
             L.crp_cuda_event_sync(e1)
             if it >= 2:
