@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <vector>
 
 #include "crp_cuda.h"
 
@@ -31,6 +32,24 @@ static inline cudaStream_t as_stream(void *s) { return (cudaStream_t) s; }
 
 // ---- SpMM plan: device CSR + auxiliary structures of the kernel variants ----
 enum { CRP_VARIANT_AUTO = 0, CRP_VARIANT_ROWSPLIT = 1, CRP_VARIANT_ROWGROUP = 2, CRP_VARIANT_MERGEPATH = 3 };
+
+// Rows of the row-split kernel with more than CRP_LONG_ROW nonzeros are cut into segments of
+// CRP_LONG_SEG nonzeros that are multiplied as independent "virtual rows" into a scratch matrix and
+// summed per row in segment order by a second kernel (deterministic, no atomics).
+enum { CRP_LONG_ROW = 1024, CRP_LONG_SEG = 512 };
+struct crp_longrows
+{
+    int       nlong;            // rows that are split (0: nothing to do)
+    int       nseg;             // segments in total
+    int       nshort;           // rows left to the plain row-split launch
+    int       *d_short;         // nshort row ids (NULL when nlong == 0)
+    int       *d_seg_beg;       // nseg: first nonzero of each segment
+    int       *d_seg_end;       // nseg: one past its last nonzero
+    int       *d_long_row;      // nlong: row id
+    int       *d_long_sptr;     // nlong + 1: segment range of each long row
+    void      *d_scratch;       // nseg x n partial results
+    size_t    scratch_bytes;
+};
 
 // row-group (register-blocked) decomposition, see spmm_rowgroup.cu
 struct crp_rowgroup
@@ -62,14 +81,16 @@ struct crp_spmm_plan
     float     *d_val32;         // nnz, created on the first fp32 exec
     int       max_row_nnz;
     double    avg_row_nnz;
-    // merge-path (nnz-balanced) decomposition, built on demand
-    int       *d_mp_rowstart;   // per work item: first row
-    int       mp_items, mp_chunk;
+    // nnz-balanced handling of very long rows (power-law matrices), see spmm_longrow.cu
+    crp_longrows lr;
     crp_rowgroup rg;
     char      kernel_name[64];
 };
 
-void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val);
+void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val, std::vector<int> *rest_out);
 void crp_rowgroup_destroy(crp_spmm_plan *plan);
+// rows: the row ids the row-split kernel is responsible for (NULL = all m rows)
+void crp_longrows_build(crp_spmm_plan *plan, const int *rowptr, const int *rows, const int nrows);
+void crp_longrows_destroy(crp_spmm_plan *plan);
 
 #endif

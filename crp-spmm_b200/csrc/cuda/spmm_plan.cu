@@ -9,9 +9,11 @@
 
 template <typename T, int VECN>
 void crp_launch_rowsplit(
-    const crp_spmm_plan *plan, const int nrows, const int *row_list, const T *val, const int n, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
-    T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
+    const crp_spmm_plan *plan, const int nrows, const int *row_list, const int *pbeg, const int *pend, const T *val, const int n,
+    const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
 );
+template <typename T>
+void crp_launch_longrow_reduce(const crp_longrows *lr, const int n, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
 template <typename T, int VEC>
 void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
 
@@ -40,7 +42,10 @@ extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, co
         CRP_CUDA_CHECK(cudaMemcpy(p->d_colidx, colidx_h, sizeof(int) * (size_t) p->nnz, cudaMemcpyHostToDevice));
         CRP_CUDA_CHECK(cudaMemcpy(p->d_val, val_h, sizeof(double) * (size_t) p->nnz, cudaMemcpyHostToDevice));
     }
-    crp_rowgroup_build(p, rowptr_h, colidx_h, val_h);
+    std::vector<int> rest;
+    crp_rowgroup_build(p, rowptr_h, colidx_h, val_h, &rest);
+    if (p->rg.R > 1) crp_longrows_build(p, rowptr_h, rest.data(), (int) rest.size());
+    else crp_longrows_build(p, rowptr_h, NULL, m);
     return p;
 }
 
@@ -51,7 +56,7 @@ extern "C" void crp_cuda_spmm_plan_destroy(crp_spmm_plan *plan)
     if (plan->d_colidx) CRP_CUDA_CHECK(cudaFree(plan->d_colidx));
     if (plan->d_val)    CRP_CUDA_CHECK(cudaFree(plan->d_val));
     if (plan->d_val32)  CRP_CUDA_CHECK(cudaFree(plan->d_val32));
-    if (plan->d_mp_rowstart) CRP_CUDA_CHECK(cudaFree(plan->d_mp_rowstart));
+    crp_longrows_destroy(plan);
     crp_rowgroup_destroy(plan);
     free(plan);
 }
@@ -72,6 +77,34 @@ static void cast_to_f32(const double *src, float **dst, size_t count, cudaStream
     CRP_LAUNCH_CHECK();
 }
 
+// the row-split kernel over a row set, with the long rows of that set cut into segments (spmm_longrow.cu)
+template <typename T, int VECN>
+static void rowsplit_balanced(
+    crp_spmm_plan *plan, const bool use_lr, const int nrows, const int *rows, const T *val, const int n,
+    const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s
+)
+{
+    const int x0_rows = plan->x0_rows;
+    crp_longrows *lr = &plan->lr;
+    if (!use_lr || lr->nlong == 0)
+    {
+        crp_launch_rowsplit<T, VECN>(plan, nrows, rows, plan->d_rowptr, plan->d_rowptr + 1, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
+        return;
+    }
+    if (lr->nshort > 0)
+        crp_launch_rowsplit<T, VECN>(plan, lr->nshort, lr->d_short, plan->d_rowptr, plan->d_rowptr + 1, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
+    const size_t need = sizeof(T) * (size_t) lr->nseg * (size_t) n;
+    if (need > lr->scratch_bytes)
+    {
+        CRP_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (lr->d_scratch) CRP_CUDA_CHECK(cudaFree(lr->d_scratch));
+        CRP_CUDA_CHECK(cudaMalloc(&lr->d_scratch, need));
+        lr->scratch_bytes = need;
+    }
+    crp_launch_rowsplit<T, VECN>(plan, lr->nseg, NULL, lr->d_seg_beg, lr->d_seg_end, val, n, X0, ldx0, x0_rows, X1, ldx1, (T) 1, (T) 0, (T *) lr->d_scratch, (size_t) n, s);
+    crp_launch_longrow_reduce<T>(lr, n, alpha, beta, C, ldc, s);
+}
+
 template <typename T, int VECN>
 static void spmm_dispatch(
     crp_spmm_plan *plan, const T *val, const T *bval, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1,
@@ -81,18 +114,20 @@ static void spmm_dispatch(
     const int x0_rows = plan->x0_rows;
     const crp_rowgroup *rg = &plan->rg;
     const bool want_rg = (plan->variant == CRP_VARIANT_AUTO || plan->variant == CRP_VARIANT_ROWGROUP);
+    const char *lr_tag = (plan->lr.nlong > 0) ? "+longrow" : "";
     if (want_rg && rg->R > 1 && rg->ngroups > 0)
     {
         const uintptr_t ptrs = (uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C;
         const bool vec_ok = (n % VECN == 0) && (ldx0 % VECN == 0) && (X1 == NULL || ldx1 % VECN == 0) && (ldc % VECN == 0) && ((ptrs & 15) == 0);
         if (vec_ok) crp_launch_rowgroup<T, VECN>(rg, bval, n / VECN, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
         else        crp_launch_rowgroup<T, 1>(rg, bval, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
-        if (rg->nrest > 0)
-            crp_launch_rowsplit<T, VECN>(plan, rg->nrest, rg->d_rest, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
-        snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowgroup_%s_R%d%s", tname, rg->R, rg->nrest > 0 ? "+rowsplit" : "");
+        if (rg->nrest > 0) rowsplit_balanced<T, VECN>(plan, true, rg->nrest, rg->d_rest, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s);
+        snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowgroup_%s_R%d%s%s", tname, rg->R, rg->nrest > 0 ? "+rowsplit" : "", rg->nrest > 0 ? lr_tag : "");
     } else {
-        crp_launch_rowsplit<T, VECN>(plan, plan->m, NULL, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s);
-        snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowsplit_%s", tname);
+        // forcing "rowsplit" on a plan that has a row-group form: the segment lists were built for the rest rows only
+        const bool use_lr = (rg->R <= 1) && plan->variant != CRP_VARIANT_ROWSPLIT;
+        rowsplit_balanced<T, VECN>(plan, use_lr, plan->m, NULL, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s);
+        snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowsplit_%s%s", tname, use_lr ? lr_tag : "");
     }
     plan->last_kernel = plan->kernel_name;
 }

@@ -62,8 +62,9 @@ static double analyse_R(const int m, const int *rowptr, const int *colidx, const
     return (double) nblk * (4.0 + R) + (double) rest * 5.0;
 }
 
-void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val)
+void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val, std::vector<int> *rest_out)
 {
+    if (rest_out) rest_out->clear();
     crp_rowgroup *rg = &plan->rg;
     memset(rg, 0, sizeof(*rg));
     const int m = plan->m;
@@ -126,6 +127,7 @@ void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colid
     rg->d_bcol = (int *) upload(b_col.data(), sizeof(int) * b_col.size());
     rg->d_bval = (double *) upload(b_val.data(), sizeof(double) * b_val.size());
     rg->d_rest = (int *) upload(rest_rows.data(), sizeof(int) * rest_rows.size());
+    if (rest_out) rest_out->swap(rest_rows);
 }
 
 void crp_rowgroup_destroy(crp_spmm_plan *plan)

@@ -37,7 +37,7 @@ template <typename T> struct vec_io<T, 1>
 
 template <typename T, int VEC, int LPR, int U>
 __global__ void __launch_bounds__(256) spmm_rowsplit_kernel(
-    const int m, const int *__restrict__ row_list, const int *__restrict__ rowptr, const int *__restrict__ colidx, const T *__restrict__ val,
+    const int m, const int *__restrict__ row_list, const int *__restrict__ pbeg, const int *__restrict__ pend, const int *__restrict__ colidx, const T *__restrict__ val,
     const int nv,                                   // 128-bit (or scalar) column groups per row
     const T *__restrict__ X0, const size_t ldx0, const int x0_rows,
     const T *__restrict__ X1, const size_t ldx1,
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) spmm_rowsplit_kernel(
     if (ridx < m)
     {
         if (row_list != NULL) row = __ldg(row_list + ridx);
-        p_beg = __ldg(rowptr + row);
-        p_end = __ldg(rowptr + row + 1);
+        p_beg = __ldg(pbeg + row);
+        p_end = __ldg(pend + row);
     }
 
     for (int v0 = 0; v0 < nv; v0 += LPR * U)
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) spmm_rowsplit_kernel(
 
 template <typename T, int VEC, int LPR, int U>
 static void launch_one(
-    const crp_spmm_plan *plan, const int nrows, const int *row_list, const T *val, const int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
+    const crp_spmm_plan *plan, const int nrows, const int *row_list, const int *pbeg, const int *pend, const T *val, const int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
     T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
 )
 {
@@ -148,17 +148,17 @@ static void launch_one(
     const long long blocks = (warps + 7) / 8;
     if (blocks == 0) return;
     spmm_rowsplit_kernel<T, VEC, LPR, U><<<(unsigned) blocks, 256, 0, stream>>>(
-        nrows, row_list, plan->d_rowptr, plan->d_colidx, val, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc);
+        nrows, row_list, pbeg, pend, plan->d_colidx, val, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc);
     CRP_LAUNCH_CHECK();
 }
 
 template <typename T, int VEC>
 static void launch_width(
-    const crp_spmm_plan *plan, const int nrows, const int *row_list, const T *val, const int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
+    const crp_spmm_plan *plan, const int nrows, const int *row_list, const int *pbeg, const int *pend, const T *val, const int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
     T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
 )
 {
-#define CRP_RS(LPR, U) launch_one<T, VEC, LPR, U>(plan, nrows, row_list, val, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, stream)
+#define CRP_RS(LPR, U) launch_one<T, VEC, LPR, U>(plan, nrows, row_list, pbeg, pend, val, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, stream)
     if (nv >= 128)     CRP_RS(32, 4);
     else if (nv >= 64) CRP_RS(32, 2);
     else if (nv > 16)  CRP_RS(32, 1);
@@ -171,15 +171,15 @@ static void launch_width(
 
 template <typename T, int VECN>
 void crp_launch_rowsplit(
-    const crp_spmm_plan *plan, const int nrows, const int *row_list, const T *val, const int n, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
+    const crp_spmm_plan *plan, const int nrows, const int *row_list, const int *pbeg, const int *pend, const T *val, const int n, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1,
     T alpha, T beta, T *C, size_t ldc, cudaStream_t stream
 )
 {
     const uintptr_t ptrs = (uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C;
     const bool vec_ok = (n % VECN == 0) && (ldx0 % VECN == 0) && (X1 == NULL || ldx1 % VECN == 0) && (ldc % VECN == 0) && ((ptrs & 15) == 0);
-    if (vec_ok) launch_width<T, VECN>(plan, nrows, row_list, val, n / VECN, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, stream);
-    else        launch_width<T, 1>(plan, nrows, row_list, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, stream);
+    if (vec_ok) launch_width<T, VECN>(plan, nrows, row_list, pbeg, pend, val, n / VECN, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, stream);
+    else        launch_width<T, 1>(plan, nrows, row_list, pbeg, pend, val, n, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, stream);
 }
 
-template void crp_launch_rowsplit<double, 2>(const crp_spmm_plan *, const int, const int *, const double *, const int, const double *, size_t, int, const double *, size_t, double, double, double *, size_t, cudaStream_t);
-template void crp_launch_rowsplit<float, 4>(const crp_spmm_plan *, const int, const int *, const float *, const int, const float *, size_t, int, const float *, size_t, float, float, float *, size_t, cudaStream_t);
+template void crp_launch_rowsplit<double, 2>(const crp_spmm_plan *, const int, const int *, const int *, const int *, const double *, const int, const double *, size_t, int, const double *, size_t, double, double, double *, size_t, cudaStream_t);
+template void crp_launch_rowsplit<float, 4>(const crp_spmm_plan *, const int, const int *, const int *, const int *, const float *, const int, const float *, size_t, int, const float *, size_t, float, float, float *, size_t, cudaStream_t);

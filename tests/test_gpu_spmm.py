@@ -52,6 +52,18 @@ def device_spmm(m, k, rowptr, colidx, val, B, dtype=np.float64, variant=b"auto",
     return out[:, :n], name
 
 
+def _longrows():
+    """A few rows far beyond CRP_LONG_ROW (1024) nonzeros among short and empty ones: the segment + reduce path."""
+    rng = np.random.default_rng(9)
+    m, k = 60, 6000
+    lens = rng.integers(0, 12, m)
+    lens[[0, 7, 59]] = [5000, 1025, 3000]
+    rows = np.repeat(np.arange(m), lens)
+    cols = np.concatenate([np.sort(rng.choice(k, int(c), replace=False)) for c in lens])
+    vals = rng.uniform(-1, 1, rows.size)
+    return (m, k) + gen.coo_to_csr(m, rows.astype(np.int64), cols.astype(np.int64), vals, sum_duplicates=False)
+
+
 @pytest.fixture(scope="module")
 def mats():
     return {
@@ -59,11 +71,12 @@ def mats():
         "pwtk": gen.pwtk_like(m=3000, target_nnz=155000, bandwidth=2500, grid_w=16, seed=3),
         "rmat": gen.rmat(scale=11, edge_factor=16, seed=5),
         "stencil": gen.stencil27(10),
+        "longrows": _longrows(),
         "onerow": (3, 900) + gen.coo_to_csr(3, np.zeros(900, np.int64), np.arange(900, dtype=np.int64), np.linspace(-1, 1, 900)),
     }
 
 
-@pytest.mark.parametrize("name", ["rand", "pwtk", "rmat", "stencil", "onerow"])
+@pytest.mark.parametrize("name", ["rand", "pwtk", "rmat", "stencil", "onerow", "longrows"])
 @pytest.mark.parametrize("n", [1, 2, 3, 8, 16, 30, 32, 64, 100, 128, 256, 320])
 def test_kernel_fp64_vs_oracle(mats, name, n):
     m, k, rp, ci, v = mats[name]
@@ -76,7 +89,7 @@ def test_kernel_fp64_vs_oracle(mats, name, n):
     assert np.all(Cd[empty] == 0.0)                      # beta = 0: rows without nonzeros are written as zeros
 
 
-@pytest.mark.parametrize("name", ["rand", "pwtk", "rmat"])
+@pytest.mark.parametrize("name", ["rand", "pwtk", "rmat", "longrows"])
 @pytest.mark.parametrize("n", [4, 24, 64, 256, 1024])
 def test_kernel_fp32_vs_oracle(mats, name, n):
     m, k, rp, ci, v = mats[name]
@@ -97,8 +110,9 @@ def test_kernel_variants(mats, name, variant):
     assert rel_err(Cd, Cref) <= TOL64, kern
 
 
-def test_alpha_beta_and_two_piece_x(mats):
-    m, k, rp, ci, v = mats["rand"]
+@pytest.mark.parametrize("name", ["rand", "longrows", "pwtk"])
+def test_alpha_beta_and_two_piece_x(mats, name):
+    m, k, rp, ci, v = mats[name]
     rng = np.random.default_rng(2)
     B, C0 = rng.uniform(-1, 1, (k, 48)), rng.uniform(-1, 1, (m, 48))
     Cref = 0.5 * oracle_spmm(m, 48, rp, ci, v, B) - 2.0 * C0
