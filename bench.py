@@ -235,6 +235,7 @@ def main():
     bytes_loc, flops_loc = pb.algorithmic_bytes()
     kern = L.rp_spmm_kernel_name(pb.rp).decode()
     t_spmm_max = capi.mpi_allreduce_max(t_spmm)
+    t_spmm_min = -capi.mpi_allreduce_max(-t_spmm)
     bytes_sum = capi.mpi_allreduce_sum(float(bytes_loc))
     recv_bytes = float(r.rB_recv_size) * r.glb_n * dtype().itemsize
     recv_max = capi.mpi_allreduce_max(recv_bytes)
@@ -302,7 +303,7 @@ def main():
                          "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": None, "peak_source": peak_src, "kernel": kern,
                          "algorithmic_bytes_per_launch": bytes_loc if nproc == 1 else bytes_sum / nproc, "kernel_ms": 1e3 * (t_spmm if nproc == 1 else t_spmm_max),
                          "kernel_gflops": flops_loc / t_spmm / 1e9 if t_spmm > 0 else 0.0},
-            "phases_ms": {"pack": 1e3 * t_pack, "exchange": 1e3 * t_a2a_max, "local_spmm": 1e3 * t_spmm_max},
+            "phases_ms": {"pack": 1e3 * t_pack, "exchange": 1e3 * t_a2a_max, "local_spmm": 1e3 * t_spmm_max, "local_spmm_min_rank": 1e3 * t_spmm_min},
             "nvlink": None if nproc == 1 or t_a2a_max <= 0 else {"recv_bytes_max": recv_max, "achieved_gbs": recv_max / t_a2a_max / 1e9, "peak_gbs": 770.0,
                                                                    "frac": recv_max / t_a2a_max / 1e9 / 770.0, "peak_source": "measured peer copy, B200_PROFILING.md"},
             "cpu_baseline": cpu,

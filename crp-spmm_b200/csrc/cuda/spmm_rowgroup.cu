@@ -29,34 +29,45 @@
 
 static const int kCandR[] = { 8, 6, 4, 3, 2 };
 
-// For a group size R: which groups are "perfect" (every row of the group has exactly the same
-// sorted column list) and what the modelled cost is.  Cost unit: L1 wavefronts per 64 B of C row
-// (4 per B-row load + 1 per row FMA'd), see DESIGN.md "row-group kernel".
-static double analyse_R(const int m, const int *rowptr, const int *colidx, const int R, std::vector<unsigned char> *perfect_out, long long *nblk_out, long long *rest_nnz_out)
+// Row i "continues" row i - 1 when both have exactly the same column list; a group of R rows starting
+// at r0 is usable ("perfect") when rows r0 + 1 .. r0 + R - 1 all continue their predecessor, the list is
+// non-empty and strictly increasing.  Groups start at row `off` + multiples of R: the first local row of a
+// rank is generally not aligned with the matrix's own block structure, so every offset is tried.
+// Cost unit: L1 wavefronts per 64 B of C row (4 per B-row load + 1 per row FMA'd), see DESIGN.md.
+struct rg_rowinfo
 {
-    const int ng = (m + R - 1) / R;
-    std::vector<unsigned char> perfect((size_t) ng, 0);
-    long long nblk = 0, rest = 0;
-    for (int g = 0; g < ng; g++)
+    std::vector<unsigned char> cont;    // row i has the same columns as row i - 1
+    std::vector<unsigned char> incr;    // row i's columns are strictly increasing and the row is not empty
+};
+
+static void rg_scan_rows(const int m, const int *rowptr, const int *colidx, rg_rowinfo *ri)
+{
+    ri->cont.assign((size_t) m, 0);
+    ri->incr.assign((size_t) m, 0);
+    for (int i = 0; i < m; i++)
     {
-        const int r0 = g * R, r1 = std::min(m, r0 + R);
-        const int len = rowptr[r0 + 1] - rowptr[r0];
-        bool ok = (r1 - r0 == R) && len > 0;
-        for (int r = r0 + 1; ok && r < r1; r++)
-        {
-            if (rowptr[r + 1] - rowptr[r] != len) { ok = false; break; }
-            if (memcmp(colidx + rowptr[r], colidx + rowptr[r0], sizeof(int) * (size_t) len) != 0) ok = false;
-        }
-        if (ok)
-        {
-            // the column list must be strictly increasing for the block order to be well defined
-            for (int p = rowptr[r0] + 1; p < rowptr[r0 + 1]; p++) if (colidx[p] <= colidx[p - 1]) { ok = false; break; }
-        }
-        perfect[(size_t) g] = ok ? 1 : 0;
-        if (ok) nblk += len;
-        else rest += rowptr[r1] - rowptr[r0];
+        const int b = rowptr[i], len = rowptr[i + 1] - b;
+        bool inc = len > 0;
+        for (int p = b + 1; inc && p < b + len; p++) if (colidx[p] <= colidx[p - 1]) inc = false;
+        ri->incr[(size_t) i] = inc;
+        if (i > 0 && len > 0 && rowptr[i] - rowptr[i - 1] == len)
+            ri->cont[(size_t) i] = (memcmp(colidx + b, colidx + rowptr[i - 1], sizeof(int) * (size_t) len) == 0);
     }
-    if (perfect_out) perfect_out->swap(perfect);
+}
+
+static inline bool rg_group_ok(const rg_rowinfo &ri, const int r0, const int R, const int m)
+{
+    if (r0 + R > m || !ri.incr[(size_t) r0]) return false;
+    for (int r = r0 + 1; r < r0 + R; r++) if (!ri.cont[(size_t) r]) return false;
+    return true;
+}
+
+static double analyse_R(const int m, const int *rowptr, const rg_rowinfo &ri, const int R, const int off, long long *nblk_out, long long *rest_nnz_out)
+{
+    long long nblk = 0;
+    for (int r0 = off; r0 + R <= m; r0 += R)
+        if (rg_group_ok(ri, r0, R, m)) nblk += rowptr[r0 + 1] - rowptr[r0];
+    const long long rest = (long long) rowptr[m] - nblk * R;
     *nblk_out = nblk;
     *rest_nnz_out = rest;
     return (double) nblk * (4.0 + R) + (double) rest * 5.0;
@@ -72,33 +83,35 @@ void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colid
     int forced = 0;
     if (const char *e = getenv("CRP_SPMM_ROWGROUP_R")) forced = atoi(e);      // 0 auto, 1 disable, else force R
     if (forced == 1) return;
+    rg_rowinfo ri;
+    rg_scan_rows(m, rowptr, colidx, &ri);
     double best_cost = (double) plan->nnz * 5.0;      // everything in the row-split kernel
-    int best_R = 1;
+    int best_R = 1, best_off = 0;
     for (int R : kCandR)
     {
         if (forced > 1 && R != forced) continue;
-        long long nblk, rest;
-        const double cost = analyse_R(m, rowptr, colidx, R, NULL, &nblk, &rest);
-        if ((forced > 1 && nblk > 0) || cost < 0.9 * best_cost) { best_cost = cost; best_R = R; if (forced > 1) break; }
+        for (int off = 0; off < R && off < m; off++)
+        {
+            long long nblk, rest;
+            const double cost = analyse_R(m, rowptr, ri, R, off, &nblk, &rest);
+            const bool take = (forced > 1) ? (nblk > 0 && (best_R == 1 || cost < best_cost)) : (cost < 0.9 * best_cost || (best_R == R && cost < best_cost));
+            if (take) { best_cost = cost; best_R = R; best_off = off; }
+        }
     }
     if (best_R == 1) return;
 
     const int R = best_R;
-    std::vector<unsigned char> perfect;
-    long long nblk, rest;
-    analyse_R(m, rowptr, colidx, R, &perfect, &nblk, &rest);
-    const int ng_all = (m + R - 1) / R;
     std::vector<int> g_row, g_ptr, b_col, rest_rows;
     std::vector<double> b_val;
     g_ptr.push_back(0);
-    b_col.reserve((size_t) nblk);
-    b_val.reserve((size_t) nblk * R);
-    for (int g = 0; g < ng_all; g++)
+    long long rest = 0;
+    for (int r = 0; r < best_off && r < m; r++) { rest_rows.push_back(r); rest += rowptr[r + 1] - rowptr[r]; }
+    for (int r0 = best_off; r0 < m; r0 += R)
     {
-        const int r0 = g * R, r1 = std::min(m, r0 + R);
-        if (!perfect[(size_t) g])
+        const int r1 = std::min(m, r0 + R);
+        if (!rg_group_ok(ri, r0, R, m))
         {
-            for (int r = r0; r < r1; r++) rest_rows.push_back(r);
+            for (int r = r0; r < r1; r++) { rest_rows.push_back(r); rest += rowptr[r + 1] - rowptr[r]; }
             continue;
         }
         g_row.push_back(r0);

@@ -52,6 +52,12 @@ def device_spmm(m, k, rowptr, colidx, val, B, dtype=np.float64, variant=b"auto",
     return out[:, :n], name
 
 
+def _row_slice(mat, r0, r1):
+    """Rows [r0, r1) of a matrix: what a rank whose first row is not aligned with the 6-row node blocks holds."""
+    m, k, rp, ci, v = mat
+    return (r1 - r0, k, (rp[r0:r1 + 1] - rp[r0]).astype(np.int32), ci[rp[r0]:rp[r1]].copy(), v[rp[r0]:rp[r1]].copy())
+
+
 def _longrows():
     """A few rows far beyond CRP_LONG_ROW (1024) nonzeros among short and empty ones: the segment + reduce path."""
     rng = np.random.default_rng(9)
@@ -72,11 +78,12 @@ def mats():
         "rmat": gen.rmat(scale=11, edge_factor=16, seed=5),
         "stencil": gen.stencil27(10),
         "longrows": _longrows(),
+        "pwtk_shift": _row_slice(gen.pwtk_like(m=3000, target_nnz=155000, bandwidth=2500, grid_w=16, seed=3), 2, 2999),
         "onerow": (3, 900) + gen.coo_to_csr(3, np.zeros(900, np.int64), np.arange(900, dtype=np.int64), np.linspace(-1, 1, 900)),
     }
 
 
-@pytest.mark.parametrize("name", ["rand", "pwtk", "rmat", "stencil", "onerow", "longrows"])
+@pytest.mark.parametrize("name", ["rand", "pwtk", "pwtk_shift", "rmat", "stencil", "onerow", "longrows"])
 @pytest.mark.parametrize("n", [1, 2, 3, 8, 16, 30, 32, 64, 100, 128, 256, 320])
 def test_kernel_fp64_vs_oracle(mats, name, n):
     m, k, rp, ci, v = mats[name]
@@ -118,6 +125,16 @@ def test_alpha_beta_and_two_piece_x(mats, name):
     Cref = 0.5 * oracle_spmm(m, 48, rp, ci, v, B) - 2.0 * C0
     Cd, _ = device_spmm(m, k, rp, ci, v, B, alpha=0.5, beta=-2.0, C0=C0, x0_rows=123)
     assert rel_err(Cd, Cref) <= TOL64
+
+
+@pytest.mark.parametrize("name", ["pwtk", "pwtk_shift"])
+def test_rowgroup_kernel_is_selected_for_block_structured_rows(mats, name):
+    """6-dof node blocks are found whatever the alignment of the first local row."""
+    m, k, rp, ci, v = mats[name]
+    B = np.random.default_rng(3).uniform(-1, 1, (k, 256))
+    Cd, kern = device_spmm(m, k, rp, ci, v, B)
+    assert "rowgroup_f64_R6" in kern, kern
+    assert rel_err(Cd, oracle_spmm(m, 256, rp, ci, v, B)) <= TOL64
 
 
 def test_linearity_and_determinism(mats):
