@@ -444,8 +444,8 @@ __device__ __forceinline__ void lds_block_vals(const T *p, T (&a)[R])
     }
 }
 
-template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE, int PF>
-__global__ void __launch_bounds__(BS) spmm_rowgroup_sv_kernel(
+template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE, int PF, int MINB>
+__global__ void __launch_bounds__(BS, MINB) spmm_rowgroup_sv_kernel(
     const int ngroups, const int *__restrict__ grow, const int *__restrict__ gptr,
     const int *__restrict__ bcol, const T *__restrict__ bval,
     const int nv,
@@ -703,13 +703,14 @@ __global__ void __launch_bounds__(BS) spmm_rowgroup_sv_kernel(
     }
 }
 
-template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE = 0, int PF = 0>
+// MINB: 128-thread CTAs are meant to run 3 per SM (<= 170 registers); without the bound ptxas spends 188 and drops to 2
+template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE = 0, int PF = 0, int MINB = (BS == 128 ? 3 : 1)>
 static void rg_launch_sv(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s)
 {
     const unsigned blocks = (unsigned) ((rg->ngroups + BS / 32 - 1) / (BS / 32));
     const unsigned chunks = (unsigned) ((nv + 32 * U - 1) / (32 * U));
     if (blocks == 0) return;
-    spmm_rowgroup_sv_kernel<T, VEC, R, U, NB, BS, CB, PIPE, PF><<<dim3(blocks, chunks), BS, 0, s>>>(
+    spmm_rowgroup_sv_kernel<T, VEC, R, U, NB, BS, CB, PIPE, PF, MINB><<<dim3(blocks, chunks), BS, 0, s>>>(
         rg->ngroups, rg->d_grow, rg->d_gptr, rg->d_bcol, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc);
     CRP_LAUNCH_CHECK();
 }
@@ -780,6 +781,12 @@ static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, 
             case 43: CRP_RGSV2(2, 4, 128, 32, 2, 0);
             case 44: CRP_RGSV2(4, 4, 128, 32, 2, 0);
             case 45: CRP_RGSV2(2, 2, 256, 32, 2, 0);
+#define CRP_RGSV3(U, NB, BS, CB, MINB) rg_launch_sv<T, VEC, R, U, NB, BS, CB, 0, 0, MINB>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, (T) 0, C, ldc, s); return true
+            case 46: CRP_RGSV3(4, 2, 128, 32, 4);
+            case 47: CRP_RGSV3(4, 1, 128, 32, 4);
+            case 48: CRP_RGSV3(4, 2, 64, 32, 7);
+            case 49: CRP_RGSV3(4, 1, 64, 32, 8);
+#undef CRP_RGSV3
 #undef CRP_RGSV2
 #undef CRP_RGSV
             default: return false;
