@@ -311,6 +311,105 @@ extern "C" void crp_cuda_copy_blocks(const crp_copy_block *blocks_d, const int n
     CRP_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------- peer-memory exchange
+extern "C" int crp_cuda_ipc_get_handle(void *dptr, void *handle64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == CRP_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaError_t err = cudaIpcGetMemHandle((cudaIpcMemHandle_t *) handle64, dptr);
+    if (err != cudaSuccess) { (void) cudaGetLastError(); return 0; }
+    return 1;
+}
+
+extern "C" void *crp_cuda_ipc_open(const void *handle64)
+{
+    void *p = NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) { (void) cudaGetLastError(); return NULL; }
+    return p;
+}
+
+extern "C" void crp_cuda_ipc_close(void *peer_ptr)
+{
+    if (peer_ptr && cudaIpcCloseMemHandle(peer_ptr) != cudaSuccess) (void) cudaGetLastError();
+}
+
+// Gather rows of the local B and store them straight into the receive buffers of the ranks that need them:
+// the "pack" and the "send" of the reference in one kernel, NVLink stores issued by the SMs (128-bit when aligned).
+template <typename V>
+__global__ void __launch_bounds__(256) put_rows_kernel(
+    const char *__restrict__ src, const size_t src_pitch, const int *__restrict__ ridx, char *const *__restrict__ dst_rows,
+    const uint32_t nrow, const uint32_t row_bytes
+)
+{
+    const uint32_t vpr = row_bytes / (uint32_t) sizeof(V);
+    const size_t total = (size_t) nrow * vpr;
+    for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t) gridDim.x * blockDim.x)
+    {
+        const uint32_t r = (uint32_t) (t / vpr), v = (uint32_t) (t - (size_t) r * vpr);
+        const V val = *reinterpret_cast<const V *>(src + (size_t) ridx[r] * src_pitch + (size_t) v * sizeof(V));
+        *reinterpret_cast<V *>(dst_rows[r] + (size_t) v * sizeof(V)) = val;
+    }
+}
+
+extern "C" void crp_cuda_put_rows(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, const int *ridx_d, void *const *dst_rows_d, void *stream)
+{
+    if (nrow <= 0 || ncol <= 0) return;
+    const size_t row_bytes = dt_size * (size_t) ncol, pitch = dt_size * (size_t) lds;
+    const int grid = copy_grid((size_t) nrow * (row_bytes / 4));
+    // destination rows are row_bytes apart inside 256-byte aligned buffers: 16-byte stores need row_bytes % 16 == 0
+    if (((uintptr_t) src & 15) == 0 && pitch % 16 == 0 && row_bytes % 16 == 0)
+        put_rows_kernel<uint4><<<grid, 256, 0, as_stream(stream)>>>((const char *) src, pitch, ridx_d, (char *const *) dst_rows_d, (uint32_t) nrow, (uint32_t) row_bytes);
+    else if (((uintptr_t) src & 7) == 0 && pitch % 8 == 0 && row_bytes % 8 == 0)
+        put_rows_kernel<uint2><<<grid, 256, 0, as_stream(stream)>>>((const char *) src, pitch, ridx_d, (char *const *) dst_rows_d, (uint32_t) nrow, (uint32_t) row_bytes);
+    else
+        put_rows_kernel<uint32_t><<<grid, 256, 0, as_stream(stream)>>>((const char *) src, pitch, ridx_d, (char *const *) dst_rows_d, (uint32_t) nrow, (uint32_t) row_bytes);
+    CRP_LAUNCH_CHECK();
+}
+
+__global__ void signal_peers_kernel(unsigned int *const *__restrict__ flag_ptrs, const int nflag, const unsigned int epoch)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nflag) return;
+    __threadfence_system();                     // the puts of the previous kernel on this stream are visible system-wide first
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag_ptrs[j]), "r"(epoch) : "memory");
+}
+
+extern "C" void crp_cuda_signal_peers(unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, void *stream)
+{
+    if (nflag <= 0) return;
+    signal_peers_kernel<<<(nflag + 63) / 64, 64, 0, as_stream(stream)>>>(flag_ptrs_d, nflag, epoch);
+    CRP_LAUNCH_CHECK();
+}
+
+// The waiting side never waits for a kernel of its own GPU: the flags are written by the peers' GPUs.
+__global__ void wait_flags_kernel(const unsigned int *flags, const int *__restrict__ wait_idx, const int nwait, const unsigned int epoch, const long long timeout_ns, int *err)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nwait) return;
+    const unsigned int *f = flags + wait_idx[j];
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;)
+    {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int) (v - epoch) >= 0) break;
+        long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { *err = 1; break; }
+        __nanosleep(200);
+    }
+}
+
+extern "C" void crp_cuda_wait_flags(const unsigned int *flags_d, const int *wait_idx_d, const int nwait, const unsigned int epoch, const double timeout_s, int *err_d, void *stream)
+{
+    if (nwait <= 0) return;
+    wait_flags_kernel<<<(nwait + 63) / 64, 64, 0, as_stream(stream)>>>(flags_d, wait_idx_d, nwait, epoch, (long long) (timeout_s * 1e9), err_d);
+    CRP_LAUNCH_CHECK();
+}
+
 // 32 x 32 shared-memory tile transpose (+1 padding: conflict-free column reads)
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_kernel(const T *__restrict__ src, size_t lds, T *__restrict__ dst, size_t ldd, int nrow, int ncol)

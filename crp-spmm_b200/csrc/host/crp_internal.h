@@ -77,6 +77,19 @@ struct crp_rp_dev
     int     ring_head, ring_count;
     double  t_h2d, t_d2h;       /* staging of host B / C (seconds, device time)                      */
     int     staged;             /* 1: exchange through pinned host memory + MPI (ranks share a GPU)  */
+    /* peer-memory transport (CRP_SPMM_TRANSPORT=2): rows are stored straight into the peers' receive buffers */
+    int     p2p;
+    void    *p2p_mem;           /* own IPC-exported allocation: [flags, 1024 B][receive half 0][receive half 1] */
+    size_t  p2p_half_bytes;
+    void    **peer_mem;         /* nproc: mapped allocations of the peers this rank sends to (else NULL)   */
+    size_t  *peer_half_bytes;   /* nproc                                                                    */
+    int     *peer_recv_off;     /* nproc: row offset of this rank's rows inside peer p's receive buffer     */
+    void    *d_dst_rows[2];     /* device tables (per buffer half): destination address of every send row  */
+    int     dst_elem_size;      /* element size the tables were built for                                   */
+    void    *d_flag_ptrs;  int n_flag;      /* addresses of this rank's arrival flag on the peers it sends to */
+    int     *d_wait_idx;   int n_wait;      /* ranks whose arrival flag this rank waits for                   */
+    int     *h_err;             /* pinned: set by the wait kernel on timeout                                */
+    unsigned int epoch;
     crp_nccl_comm *nc;          /* NCCL communicator used for the B-row exchange                     */
     int     *peer_nc_rank;      /* nproc: rank of each member of rp->comm inside nc                  */
 };

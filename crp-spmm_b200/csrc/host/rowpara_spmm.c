@@ -179,6 +179,121 @@ static void rp_build_plan(
 
 /* ------------------------------------------------------------- device state */
 
+#ifndef CRP_DEFAULT_TRANSPORT
+#define CRP_DEFAULT_TRANSPORT 0
+#endif
+enum { CRP_P2P_HDR = 1024 };
+
+/*
+ * Peer-memory transport: every rank exports one allocation (arrival flags + two receive halves) with
+ * CUDA IPC, maps the allocations of the ranks it sends to, and learns at which row of their receive
+ * buffer its rows start.  Collective over rp->comm.  Returns 0 (and leaves d->p2p = 0 on every rank)
+ * if any rank could not export or map - the exchange then falls back to NCCL.
+ */
+static int rp_p2p_setup(rp_spmm_p rp, struct crp_rp_dev *d)
+{
+    const int nproc = rp->nproc, me = rp->my_rank, n = rp->glb_n;
+    int ok = (nproc <= CRP_P2P_HDR / (int) sizeof(unsigned int)) ? 1 : 0;
+    d->p2p_half_bytes = (((size_t) d->n_recv_rows * (size_t) n * sizeof(double)) + 255) & ~(size_t) 255;
+    crp_cuda_malloc_dev(&d->p2p_mem, CRP_P2P_HDR + 2 * d->p2p_half_bytes);
+    crp_cuda_memset_dev(d->p2p_mem, 0, CRP_P2P_HDR);
+    crp_cuda_device_sync();
+    struct { unsigned char h[CRP_IPC_HANDLE_BYTES]; unsigned long long half; int ok; int pad; } mine, *all;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = ok && crp_cuda_ipc_get_handle(d->p2p_mem, mine.h);
+    mine.half = (unsigned long long) d->p2p_half_bytes;
+    all = xmalloc(sizeof(mine) * (size_t) nproc);
+    MPI_Allgather(&mine, (int) sizeof(mine), MPI_BYTE, all, (int) sizeof(mine), MPI_BYTE, rp->comm);
+    /* where do my rows start in each peer's receive buffer? = that peer's recv_rows[me] */
+    d->peer_recv_off = (int *) xmalloc(sizeof(int) * (size_t) nproc);
+    MPI_Alltoall(d->recv_rows, 1, MPI_INT, d->peer_recv_off, 1, MPI_INT, rp->comm);
+    d->peer_mem = (void **) calloc((size_t) nproc, sizeof(void *));
+    d->peer_half_bytes = (size_t *) calloc((size_t) nproc, sizeof(size_t));
+    ok = 1;
+    for (int p = 0; p < nproc; p++)
+    {
+        if (!all[p].ok) ok = 0;
+        d->peer_half_bytes[p] = (size_t) all[p].half;
+    }
+    for (int p = 0; ok && p < nproc; p++)
+    {
+        /* neighbours = ranks this rank exchanges rows with in either direction (the relation is symmetric) */
+        if (p == me || (d->send_rows[p + 1] == d->send_rows[p] && d->recv_rows[p + 1] == d->recv_rows[p])) continue;
+        d->peer_mem[p] = crp_cuda_ipc_open(all[p].h);
+        if (d->peer_mem[p] == NULL) ok = 0;
+    }
+    free(all);
+    int all_ok = 0;
+    MPI_Allreduce(&ok, &all_ok, 1, MPI_INT, MPI_MIN, rp->comm);
+    if (!all_ok)
+    {
+        for (int p = 0; p < nproc; p++) crp_cuda_ipc_close(d->peer_mem[p]);
+        MPI_Barrier(rp->comm);
+        crp_cuda_free_dev(d->p2p_mem);
+        free(d->peer_mem); free(d->peer_half_bytes); free(d->peer_recv_off);
+        d->p2p_mem = NULL; d->peer_mem = NULL; d->peer_half_bytes = NULL; d->peer_recv_off = NULL;
+        if (me == 0) WARNING_PRINTF("CUDA IPC peer mapping failed; the B-row exchange falls back to NCCL\n");
+        return 0;
+    }
+    /* arrival flags: mine on every peer I send to; the ones I wait for */
+    void **fp = (void **) xmalloc(sizeof(void *) * (size_t) nproc);
+    int *wi = (int *) xmalloc(sizeof(int) * (size_t) nproc);
+    d->n_flag = d->n_wait = 0;
+    for (int p = 0; p < nproc; p++)
+    {
+        if (p == me) continue;
+        /* flags go both ways between neighbours even if rows go one way only: a rank that has seen epoch e - 1
+         * from a neighbour knows the neighbour is done reading the buffer half that epoch e will overwrite */
+        if (d->peer_mem[p] == NULL) continue;
+        fp[d->n_flag++] = (char *) d->peer_mem[p] + sizeof(unsigned int) * (size_t) me;
+        wi[d->n_wait++] = p;
+    }
+    if (d->n_flag) { crp_cuda_malloc_dev(&d->d_flag_ptrs, sizeof(void *) * (size_t) d->n_flag); crp_cuda_memcpy_h2d(fp, d->d_flag_ptrs, sizeof(void *) * (size_t) d->n_flag); }
+    if (d->n_wait) { crp_cuda_malloc_dev((void **) &d->d_wait_idx, sizeof(int) * (size_t) d->n_wait); crp_cuda_memcpy_h2d(wi, d->d_wait_idx, sizeof(int) * (size_t) d->n_wait); }
+    free(fp);
+    free(wi);
+    crp_cuda_malloc_host((void **) &d->h_err, sizeof(int));
+    *d->h_err = 0;
+    d->epoch = 0;
+    d->dst_elem_size = 0;
+    MPI_Barrier(rp->comm);
+    return 1;
+}
+
+/* destination address of every send row, for both receive halves, for the given element size */
+static void rp_p2p_tables(rp_spmm_p rp, struct crp_rp_dev *d, const int elem_size)
+{
+    if (d->dst_elem_size == elem_size || d->n_send_rows == 0) { d->dst_elem_size = elem_size; return; }
+    const size_t row_bytes = (size_t) elem_size * (size_t) rp->glb_n;
+    void **tab = (void **) xmalloc(sizeof(void *) * (size_t) d->n_send_rows);
+    for (int half = 0; half < 2; half++)
+    {
+        for (int p = 0; p < rp->nproc; p++)
+            for (int i = d->send_rows[p]; i < d->send_rows[p + 1]; i++)
+                tab[i] = (char *) d->peer_mem[p] + CRP_P2P_HDR + (size_t) half * d->peer_half_bytes[p]
+                       + row_bytes * ((size_t) d->peer_recv_off[p] + (size_t) (i - d->send_rows[p]));
+        if (d->d_dst_rows[half] == NULL) crp_cuda_malloc_dev(&d->d_dst_rows[half], sizeof(void *) * (size_t) d->n_send_rows);
+        crp_cuda_memcpy_h2d(tab, d->d_dst_rows[half], sizeof(void *) * (size_t) d->n_send_rows);
+    }
+    free(tab);
+    d->dst_elem_size = elem_size;
+}
+
+static void rp_p2p_teardown(rp_spmm_p rp, struct crp_rp_dev *d)
+{
+    if (!d->p2p) return;
+    for (int p = 0; p < rp->nproc; p++) crp_cuda_ipc_close(d->peer_mem[p]);
+    MPI_Barrier(rp->comm);          /* nobody frees an allocation a peer still has mapped */
+    crp_cuda_free_dev(d->p2p_mem);
+    crp_cuda_free_dev(d->d_dst_rows[0]);
+    crp_cuda_free_dev(d->d_dst_rows[1]);
+    crp_cuda_free_dev(d->d_flag_ptrs);
+    crp_cuda_free_dev(d->d_wait_idx);
+    crp_cuda_free_host(d->h_err);
+    free(d->peer_mem); free(d->peer_half_bytes); free(d->peer_recv_off);
+}
+
+
 /*
  * Upload the local A with virtual column ids and the send list; size the
  * persistent exchange buffers.  n_send_rows / n_recv_rows are recomputed from
@@ -229,9 +344,11 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     int wsize = 1;
     MPI_Comm_size(MPI_COMM_WORLD, &wsize);
     int transport;
-    GET_ENV_INT_VAR(transport, "CRP_SPMM_TRANSPORT", "transport", -1, 0, 1, 0);   /* 0 NCCL, 1 staged MPI */
-    if (transport < 0) transport = (wsize > crp_cuda_device_count()) ? 1 : 0;
-    d->staged = transport;
+    GET_ENV_INT_VAR(transport, "CRP_SPMM_TRANSPORT", "transport", -1, 0, 2, 0);   /* 0 NCCL, 1 staged MPI, 2 NVLink peer stores */
+    if (wsize > crp_cuda_device_count()) transport = 1;
+    else if (transport < 0) transport = CRP_DEFAULT_TRANSPORT;
+    d->staged = (transport == 1);
+    d->p2p = (transport == 2 && nproc > 1);
 
     /* Overlap mode (default with NCCL): the product is split by column into the part that needs only
      * this rank's own B rows - it runs while the exchange is in flight - and the part that needs
@@ -282,7 +399,8 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
 
     d->nc = NULL;
     d->peer_nc_rank = NULL;
-    if (nproc > 1 && !d->staged)
+    if (d->p2p) d->p2p = rp_p2p_setup(rp, d);
+    if (nproc > 1 && !d->staged && !d->p2p)
     {
         d->nc = crp_nccl_get(nccl_parent);
         d->peer_nc_rank = crp_comm_ranks_in_parent(rp->comm, nccl_parent);
@@ -295,6 +413,7 @@ static void rp_free_device_state(rp_spmm_p rp)
     if (d == NULL) return;
     crp_cuda_stream_sync(d->stream);
     crp_cuda_stream_sync(d->stream2);
+    rp_p2p_teardown(rp, d);
     crp_cuda_spmm_plan_destroy(d->plan);
     crp_cuda_spmm_plan_destroy(d->plan_off);
     crp_cuda_free_dev(d->d_sridxs);
@@ -516,15 +635,31 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         CRP_MARK(CRP_EV_B_IN, 1);                               /* fork point: B is in place */
         crp_cuda_stream_wait_event(cs, mark[CRP_EV_B_IN]);
     }
-    if (d->n_send_rows > 0 && n > 0)
+    const void *X1 = d->d_recvbuf;
+    if (d->p2p && n > 0)
     {
-        grow_dev(&d->d_sendbuf, &d->sendbuf_bytes, row_bytes * (size_t) d->n_send_rows);
-        crp_cuda_gather_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, d->d_sendbuf, n, cs);
+        /* gather + NVLink stores into the peers' receive halves, arrival flags, wait for the neighbours' flags */
+        rp_p2p_tables(rp, d, elem_size);
+        d->epoch++;
+        const int half = (int) (d->epoch & 1u);
+        if (d->n_send_rows > 0) crp_cuda_put_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, (void *const *) d->d_dst_rows[half], cs);
+        CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0, cs);
+        crp_cuda_signal_peers((unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, cs);
+        crp_cuda_wait_flags((const unsigned int *) d->p2p_mem, d->d_wait_idx, d->n_wait, d->epoch, 20.0, d->h_err, cs);
+        CRP_MARK_ON(CRP_EV_XCHG, overlap || d->n_flag > 0, cs);
+        X1 = (const char *) d->p2p_mem + CRP_P2P_HDR + (size_t) half * d->p2p_half_bytes;
+    } else {
+        if (d->n_send_rows > 0 && n > 0)
+        {
+            grow_dev(&d->d_sendbuf, &d->sendbuf_bytes, row_bytes * (size_t) d->n_send_rows);
+            crp_cuda_gather_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, d->d_sendbuf, n, cs);
+        }
+        if (d->n_recv_rows > 0 && n > 0) grow_dev(&d->d_recvbuf, &d->recvbuf_bytes, row_bytes * (size_t) d->n_recv_rows);
+        CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0 && n > 0, cs);
+        if (n > 0) rp_exchange(rp, d, row_bytes, cs);
+        CRP_MARK_ON(CRP_EV_XCHG, overlap || (rp->nproc > 1 && (d->n_send_rows > 0 || d->n_recv_rows > 0) && n > 0), cs);
+        X1 = d->d_recvbuf;
     }
-    if (d->n_recv_rows > 0 && n > 0) grow_dev(&d->d_recvbuf, &d->recvbuf_bytes, row_bytes * (size_t) d->n_recv_rows);
-    CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0 && n > 0, cs);
-    if (n > 0) rp_exchange(rp, d, row_bytes, cs);
-    CRP_MARK_ON(CRP_EV_XCHG, overlap || (rp->nproc > 1 && (d->n_send_rows > 0 || d->n_recv_rows > 0) && n > 0), cs);
 
     /* ---- local product, reading own rows from Bd and remote rows from the receive buffer ---- */
     void *Cd = C;
@@ -539,15 +674,15 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     if (!overlap)
     {
         mark[CRP_EV_DIAG] = mark[CRP_EV_OFF0] = mark[CRP_EV_XCHG];
-        if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
+        if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd, stream);
         CRP_MARK(CRP_EV_SPMM, m > 0 && n > 0);
     } else {
-        if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 0.0, Cd, (int) ldCd, stream);
+        if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd, stream);
         CRP_MARK(CRP_EV_DIAG, 1);
         crp_cuda_stream_wait_event(stream, mark[CRP_EV_XCHG]);  /* join: received rows are in place, sends are done */
         CRP_MARK(CRP_EV_OFF0, 1);
         if (m > 0 && n > 0 && d->plan_off != NULL)
-            crp_cuda_spmm_exec(d->plan_off, n, elem_size, 1.0, Bd, (int) ldBd, d->d_recvbuf, n, 1.0, Cd, (int) ldCd, stream);
+            crp_cuda_spmm_exec(d->plan_off, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 1.0, Cd, (int) ldCd, stream);
         CRP_MARK(CRP_EV_SPMM, 1);
     }
 
@@ -582,6 +717,12 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     {
         crp_cuda_event_sync(mark[CRP_EV_END]);
         d->ring_host_t1[k] = get_wtime_sec();
+        if (d->p2p && *d->h_err)
+        {
+            fprintf(stderr, "[FATAL] rp_spmm_exec: a neighbour's B rows did not arrive within 20 s (peer-memory transport)\n");
+            fflush(stderr);
+            abort();
+        }
         rp_collect(rp, 1);
     }
 }

@@ -94,6 +94,19 @@ void crp_cuda_copy_blocks(const crp_copy_block *blocks_d, const int nblk, const 
 /* dst (ncol x nrow, leading dimension ldd) := transpose of src (nrow x ncol, leading dimension lds) */
 void crp_cuda_transpose(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, void *dst, const int ldd, void *stream);
 
+/* ---- peer-memory exchange over NVLink (one process per GPU; replaces the MPI P2P ring / MPI_Alltoallv of
+ * B rows at reference src/rowpara_spmm.c:280-308 with direct stores into the peers' receive buffers) ---- */
+enum { CRP_IPC_HANDLE_BYTES = 64 };
+int   crp_cuda_ipc_get_handle(void *dptr, void *handle64);      /* 1 on success (dptr must come from crp_cuda_malloc_dev) */
+void *crp_cuda_ipc_open(const void *handle64);                  /* NULL on failure; enables peer access lazily            */
+void  crp_cuda_ipc_close(void *peer_ptr);
+/* dst_rows_d[i] (a device array of peer addresses) := src[ridx_d[i], 0:ncol]; one launch for all peers */
+void  crp_cuda_put_rows(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, const int *ridx_d, void *const *dst_rows_d, void *stream);
+/* after the puts (same stream): *flag_ptrs_d[j] := epoch for j < nflag, with system-scope release */
+void  crp_cuda_signal_peers(unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, void *stream);
+/* spin until every flags_d[wait_idx_d[j]] has reached epoch, j < nwait; on timeout (seconds) *err_d is set to 1 and the kernel returns */
+void  crp_cuda_wait_flags(const unsigned int *flags_d, const int *wait_idx_d, const int nwait, const unsigned int epoch, const double timeout_s, int *err_d, void *stream);
+
 /* ---- local SpMM ---- */
 typedef struct crp_spmm_plan crp_spmm_plan;
 
