@@ -105,6 +105,16 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this kernel, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f).get(f"{workload}:{kernel}")
+        return None if e is None else e["dram_read_bytes"] + e["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def run_reference_cpu(csr, n, mode, steps, nranks=4):
     """The reference sources under oracle/_ref on the host cores: returns (gflops, seconds per exec, cores, sample)."""
     ref = os.path.join(ROOT, "oracle", "_ref")
@@ -167,6 +177,7 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm (B200)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     from pycrp import capi
     from pycrp.flow import Problem
     L = capi.load()
@@ -300,7 +311,7 @@ def main():
                        "overlap": os.environ.get("CRP_SPMM_OVERLAP", "auto") if nproc > 1 else "n/a"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ach if nproc == 1 else ach_job, "peak": peak, "unit": "GB/s",
-                         "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": None, "peak_source": peak_src, "kernel": kern,
+                         "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": measured_traffic(a.workload, kern) if nproc == 1 else None, "peak_source": peak_src, "kernel": kern,
                          "algorithmic_bytes_per_launch": bytes_loc if nproc == 1 else bytes_sum / nproc, "kernel_ms": 1e3 * (t_spmm if nproc == 1 else t_spmm_max),
                          "kernel_gflops": flops_loc / t_spmm / 1e9 if t_spmm > 0 else 0.0},
             "phases_ms": {"pack": 1e3 * t_pack, "exchange": 1e3 * t_a2a_max, "local_spmm": 1e3 * t_spmm_max, "local_spmm_min_rank": 1e3 * t_spmm_min},

@@ -179,8 +179,11 @@ static void rp_build_plan(
 
 /* ------------------------------------------------------------- device state */
 
+/* Default data plane with one rank per GPU: 2 = NVLink peer stores (measured on the pwtk-shaped n = 256 case:
+ * 8 GPUs 0.134 vs 0.150 ms per exec with NCCL, 2 GPUs 0.271 vs 0.277; profiles/r01_bench_n*_{p2p,nccl}.json).
+ * Falls back to NCCL by itself when CUDA IPC is not available. */
 #ifndef CRP_DEFAULT_TRANSPORT
-#define CRP_DEFAULT_TRANSPORT 0
+#define CRP_DEFAULT_TRANSPORT 2
 #endif
 enum { CRP_P2P_HDR = 1024 };
 
