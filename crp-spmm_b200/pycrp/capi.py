@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_DIR = os.environ.get("CRP_LIB_DIR") or os.path.join(PKG_DIR, "lib")      # CRP_LIB_DIR: alternative build (sanitizer runs)
 BIN_DIR = os.path.join(PKG_DIR, "bin")
 
 # ---- mini-MPI handles (crp-spmm_b200/minimpi/mpi.h) ----
