@@ -728,6 +728,11 @@ static void rg_launch_one(const crp_rowgroup *rg, const T *bval, int nv, const T
     CRP_LAUNCH_CHECK();
 }
 
+bool crp_launch_rowgroup_x(
+    const int cfg, const crp_rowgroup *rg, const double *bval, const int n, const double *X0, const size_t ldx0,
+    const double *X1, const double alpha, const double beta, double *C, const size_t ldc, cudaStream_t s
+);
+
 // development sweep (CRP_SPMM_RG_CFG = index): fp64, 128-bit, R = 6, full-warp groups only
 template <typename T, int VEC, int R>
 static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
@@ -736,6 +741,7 @@ static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, 
     {
         const char *e = getenv("CRP_SPMM_RG_CFG");
         if (e == NULL || nv < 128) return false;
+        if (atoi(e) >= 60) return crp_launch_rowgroup_x(atoi(e), rg, bval, nv * VEC, X0, ldx0, X1, alpha, 0.0, C, ldc, s);   // spmm_rowgroup_x.cu
 #define CRP_RGX(U, NB, PIPE, PF, BS) rg_launch_one<T, VEC, R, 32, U, NB, PIPE, PF, BS>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s); return true
         switch (atoi(e))
         {
