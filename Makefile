@@ -20,7 +20,7 @@ CFLAGS  := -O2 -g -std=gnu11 -fPIC -fopenmp -Wall -Wno-unused-function -I$(ROOT)
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function \
            -I$(ROOT)/include -I$(SRC)/cuda $(CRP_NVCC_EXTRA)
 
-HOST_SRC := utils.c spmat_part.c dev_type.c crp_common.c rowpara_spmm.c para2d_spmm.c mat_redist.c
+HOST_SRC := utils.c spmat_part.c dev_type.c crp_common.c rowpara_spmm.c para2d_spmm.c mat_redist.c crpspmm.c
 COMM_SRC := crp_nccl.c
 CUDA_SRC := $(notdir $(wildcard $(SRC)/cuda/*.cu))
 OBJS := $(addprefix $(OBJDIR)/host_,$(HOST_SRC:.c=.o)) $(addprefix $(OBJDIR)/comm_,$(COMM_SRC:.c=.o)) $(addprefix $(OBJDIR)/cuda_,$(CUDA_SRC:.cu=.o))
@@ -58,13 +58,16 @@ DRV_OBJS := $(addprefix $(OBJDIR)/drv_,$(DRV_HELP:.c=.o)) $(OBJDIR)/drv_mkl_stan
 DRV_CFLAGS := -O3 -march=x86-64-v3 -fopenmp -std=gnu11 -g -DUSE_MKL -Wno-unused-result
 
 ifneq ($(wildcard $(REF)/examples/test_para2d_spmm.c),)
-drivers: lib $(BINDIR)/test_para2d_spmm.exe $(BINDIR)/test_rp_spmm.exe $(BINDIR)/test_spmm_2dpg.exe
+drivers: lib $(BINDIR)/test_para2d_spmm.exe $(BINDIR)/test_rp_spmm.exe $(BINDIR)/test_spmm_2dpg.exe $(BINDIR)/test_crpspmm.exe
 else
 drivers:
 	@echo "drivers: $(REF) not present - keeping prebuilt drivers (if any)"
 endif
 
 $(OBJDIR)/drv_%.o: $(REF)/examples/%.c | $(OBJDIR)
+	$(CC) $(DRV_CFLAGS) $(DRV_INC) -c $< -o $@
+# the deprecated composite-engine driver, also unchanged (deprecated/examples/test_crpspmm.c) against include/crpspmm.h
+$(OBJDIR)/drv_test_crpspmm.o: $(REF)/deprecated/examples/test_crpspmm.c | $(OBJDIR)
 	$(CC) $(DRV_CFLAGS) $(DRV_INC) -c $< -o $@
 $(OBJDIR)/drv_mkl_standin.o: $(ROOT)/oracle/stubs/mkl_standin.c | $(OBJDIR)
 	$(CC) $(DRV_CFLAGS) -ffp-contract=off $(DRV_INC) -c $< -o $@

@@ -683,6 +683,32 @@ int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm *newcomm)
     return MPI_SUCCESS;
 }
 
+/* Balanced factorisation of nnodes over the entries of dims[] that are 0 (non-increasing order), as MPI specifies. */
+int MPI_Dims_create(int nnodes, int ndims, int dims[])
+{
+    int fixed = 1, nfree = 0;
+    for (int i = 0; i < ndims; i++) { if (dims[i] > 0) fixed *= dims[i]; else nfree++; }
+    if (nfree == 0) return MPI_SUCCESS;
+    if (fixed <= 0 || nnodes % fixed != 0) fatal("MPI_Dims_create: %d nodes cannot be split with the given fixed dimensions", nnodes);
+    int rest = nnodes / fixed;
+    int *out = (int *) malloc(sizeof(int) * (size_t) nfree);
+    for (int i = 0; i < nfree; i++) out[i] = 1;
+    /* hand the prime factors, largest first, to the currently smallest dimension */
+    int primes[64], np = 0;
+    for (int d = 2; rest > 1; ) { if (rest % d == 0) { primes[np++] = d; rest /= d; } else d++; }
+    for (int i = np - 1; i >= 0; i--)
+    {
+        int small = 0;
+        for (int j = 1; j < nfree; j++) if (out[j] < out[small]) small = j;
+        out[small] *= primes[i];
+    }
+    for (int i = 0; i < nfree; i++)                 /* sort non-increasing */
+        for (int j = i + 1; j < nfree; j++) if (out[j] > out[i]) { int t = out[i]; out[i] = out[j]; out[j] = t; }
+    for (int i = 0, j = 0; i < ndims; i++) if (dims[i] <= 0) dims[i] = out[j++];
+    free(out);
+    return MPI_SUCCESS;
+}
+
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *newcomm)
 {
     comm_t *c = get_comm(comm);

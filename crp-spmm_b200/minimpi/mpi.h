@@ -97,6 +97,7 @@ int MPI_Comm_size(MPI_Comm comm, int *size);
 int MPI_Comm_rank(MPI_Comm comm, int *rank);
 int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm *newcomm);
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *newcomm);
+int MPI_Dims_create(int nnodes, int ndims, int dims[]);
 int MPI_Comm_free(MPI_Comm *comm);
 int MPI_Dist_graph_create_adjacent(
     MPI_Comm comm_old, int indegree, const int *sources, const int *sourceweights,

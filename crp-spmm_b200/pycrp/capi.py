@@ -78,6 +78,24 @@ class MatRedistEngine(C.Structure):
     ]
 
 
+class CrpspmmEngine(C.Structure):
+    """struct crpspmm_engine of include/crpspmm.h (public part)."""
+    _fields_ = [
+        ("np_glb", C.c_int), ("rank_glb", C.c_int), ("np_row", C.c_int), ("np_col", C.c_int), ("rank_row", C.c_int), ("rank_col", C.c_int),
+        ("glb_m", C.c_int), ("glb_n", C.c_int), ("glb_k", C.c_int),
+        ("loc_A_srow", C.c_int), ("loc_A_erow", C.c_int), ("loc_A_nrow", C.c_int), ("loc_A_nnz", C.c_int),
+        ("loc_B_srow", C.c_int), ("loc_B_erow", C.c_int), ("loc_B_scol", C.c_int), ("loc_B_ecol", C.c_int),
+        ("loc_B_nrow", C.c_int), ("loc_B_ncol", C.c_int), ("loc_C_srow", C.c_int), ("loc_C_nrow", C.c_int),
+        ("alloc_workbuf", C.c_int), ("use_CUDA", C.c_int),
+        ("loc_A_rowptr", c_int_p), ("loc_A_colidx", c_int_p), ("loc_A_val", c_double_p),
+        ("comm_glb", C.c_int), ("rd_B", C.POINTER(MatRedistEngine)), ("rd_C", C.POINTER(MatRedistEngine)), ("p2d", C.POINTER(Para2dSpmm)),
+        ("n_exec", C.c_int), ("t_init", C.c_double), ("t_exec", C.c_double), ("t_rd_A", C.c_double), ("t_agv_A", C.c_double),
+        ("t_rd_B", C.c_double), ("t_a2a_B", C.c_double), ("t_spmm", C.c_double), ("t_rd_C", C.c_double), ("t_exec_nr", C.c_double),
+        ("nelem_A_rd", C.c_size_t), ("nelem_A_agv", C.c_size_t), ("nelem_B_rd", C.c_size_t), ("nelem_B_a2av", C.c_size_t),
+        ("nelem_B_a2av_min", C.c_size_t), ("priv", C.c_void_p),
+    ]
+
+
 # every symbol include/*.h declares (tests/test_cabi_symbols.py checks the library exports them all)
 EXPORTS = {
     "utils.h": ["get_wtime_sec", "calc_block_spos_size", "malloc_aligned", "free_aligned", "calc_2norm", "calc_err_2norm",
@@ -88,6 +106,8 @@ EXPORTS = {
     "rowpara_spmm.h": ["rp_spmm_init", "rp_spmm_free", "rp_spmm_exec", "rp_spmm_print_stat", "rp_spmm_clear_stat"],
     "para2d_spmm.h": ["para2d_spmm_init", "para2d_spmm_free", "para2d_spmm_exec", "para2d_spmm_print_stat", "para2d_spmm_clear_stat"],
     "mat_redist.h": ["mat_redist_engine_init", "mat_redist_engine_attach_workbuf", "mat_redist_engine_exec", "mat_redist_engine_free"],
+    "crpspmm.h": ["crpspmm_engine_init", "crpspmm_engine_attach_workbuf", "crpspmm_engine_exec", "crpspmm_engine_free",
+                  "crpspmm_engine_print_stat", "crpspmm_engine_clear_stat"],
 }
 
 _lib = None
@@ -138,6 +158,12 @@ def load():
     L.mat_redist_engine_attach_workbuf.argtypes = [C.POINTER(MatRedistEngine), vp, vp]
     L.mat_redist_engine_exec.argtypes = [C.POINTER(MatRedistEngine), vp, i, vp, i]
     L.mat_redist_engine_free.argtypes = [C.POINTER(C.POINTER(MatRedistEngine))]
+    L.crpspmm_engine_init.argtypes = [i, i, i, i, i, vp, vp, i, i, i, i, i, i, i, i, i, i, C.POINTER(C.POINTER(CrpspmmEngine)), C.POINTER(sz)]
+    L.crpspmm_engine_exec.argtypes = [C.POINTER(CrpspmmEngine), vp, vp, vp, vp, i, vp, i]
+    L.crpspmm_engine_free.argtypes = [C.POINTER(C.POINTER(CrpspmmEngine))]
+    L.crpspmm_engine_print_stat.argtypes = [C.POINTER(CrpspmmEngine)]
+    L.crpspmm_engine_clear_stat.argtypes = [C.POINTER(CrpspmmEngine)]
+    L.crpspmm_engine_redist_A_values.argtypes = [C.POINTER(CrpspmmEngine), vp]
     L.is_dev_type_valid.argtypes = [i]
     L.dev_type_malloc.argtypes = [sz, i]
     L.dev_type_malloc.restype = vp

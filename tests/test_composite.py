@@ -1,0 +1,84 @@
+"""The composite engine (include/crpspmm.h): A, B, C in the caller's layouts.
+CPU: the grid is the live cost model's, and the A redistribution delivers exactly the owned rows (pattern and values).
+GPU: C in the caller's layout against scipy / the reference driver's own check."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle_lib as O
+from pycrp import gen
+from util import MINIMPIRUN, PKG
+
+UNVERIFIED = "written after the round-1 GPU budget was spent: the device path of the composite has not run on a GPU yet"
+
+
+def run(tmp_path, csr, n, nproc, *extra, plan_only=False):
+    prefix = os.path.join(str(tmp_path), "cmp")
+    env = dict(os.environ, PYTHONPATH=PKG, OMP_NUM_THREADS="2")
+    if plan_only:
+        env["CRP_SPMM_PLAN_ONLY"] = "1"
+    r = subprocess.run([MINIMPIRUN, "-np", str(nproc), sys.executable, "-m", "pycrp.composite_flow", csr, str(n), prefix, *extra],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return [dict(np.load(f"{prefix}.r{i}.npz")) for i in range(nproc)], r.stdout
+
+
+@pytest.mark.parametrize("nproc,n,split,shape", [(1, 8, "even", (120, 120)), (4, 16, "even", (300, 300)), (6, 24, "skew", (300, 300)),
+                                                 (8, 64, "skew", (256, 256)), (5, 12, "even", (200, 350)), (8, 32, "even", (350, 200))])
+def test_plan_and_A_redistribution(nproc, n, split, shape, tmp_path):
+    m, k = shape
+    mm, kk, rp, ci, v = gen.random_rect(m, k, 7, seed=nproc * 7 + n, empty_rows=(2, 50))
+    csr = os.path.join(str(tmp_path), "a.bin")
+    gen.write_csr_bin(csr, mm, kk, rp, ci, v)
+    dumps, _ = run(tmp_path, csr, n, nproc, "--no-exec", "--rowsplit", split, plan_only=True)
+    rb = O.row_partition(rp, nproc)
+    ref = O.part2d(nproc, mm, n, kk, rb, rp, ci)              # what the reference's live cost model chooses for this matrix
+    for r, d in enumerate(dumps):
+        assert (int(d["np_row"]), int(d["np_col"])) == (ref["pm"], ref["pn"])
+        a0, a1 = int(ref["A0_rowptr"][r]), int(ref["A0_rowptr"][r + 1])
+        assert (int(d["loc_A_srow"]), int(d["loc_A_nrow"])) == (a0, a1 - a0)
+        assert np.array_equal(d["loc_A_rowptr"], rp[a0:a1 + 1])                       # global nnz offsets kept
+        assert np.array_equal(d["loc_A_colidx"], ci[rp[a0]:rp[a1]])
+        assert np.array_equal(d["loc_A_val"], v[rp[a0]:rp[a1]])
+        pi, pj = r // ref["pn"], r % ref["pn"]
+        assert list(d["loc_B"]) == [ref["B_rowptr"][pi], ref["B_rowptr"][pi + 1] - ref["B_rowptr"][pi],
+                                    ref["BC_colptr"][pj], ref["BC_colptr"][pj + 1] - ref["BC_colptr"][pj]]
+        assert list(d["loc_C"]) == [ref["AC_rowptr"][pi], ref["AC_rowptr"][pi + 1] - ref["AC_rowptr"][pi]]
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason=UNVERIFIED)
+@pytest.mark.parametrize("nproc,n,split,gather", [(1, 8, "even", False), (4, 16, "skew", False), (6, 24, "even", True)])
+def test_composite_exec(nproc, n, split, gather, tmp_path):
+    mm, kk, rp, ci, v = gen.random_rect(300, 300, 7, seed=nproc, empty_rows=())
+    csr = os.path.join(str(tmp_path), "a.bin")
+    gen.write_csr_bin(csr, mm, kk, rp, ci, v)
+    extra = ["--rowsplit", split] + (["--gather-c"] if gather else [])
+    dumps, out = run(tmp_path, csr, n, nproc, *extra)
+    Cref = sp.csr_matrix((v, ci, rp), shape=(mm, kk)) @ gen.fill_B(0, kk, 0, n)
+    num = den = 0.0
+    for d in dumps:
+        r0, nr, c0, nc = (int(x) for x in d["C_rect"])
+        num += float(np.sum((d["C"] - Cref[r0:r0 + nr, c0:c0 + nc]) ** 2)); den += float(np.sum(Cref[r0:r0 + nr, c0:c0 + nc] ** 2))
+    assert np.sqrt(num) <= 1e-12 * np.sqrt(den)
+    assert "Communicated Matrix Elements" in out and "Redist C to user's 2D layout" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason=UNVERIFIED)
+def test_deprecated_driver_runs_unchanged(tmp_path):
+    exe = os.path.join(PKG, "bin", "test_crpspmm.exe")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    m, k, rp, ci, v = gen.pwtk_like(m=1500, target_nnz=77000, bandwidth=1200, grid_w=10, seed=5)
+    mtx = os.path.join(str(tmp_path), "small.mtx")
+    gen.write_mtx(mtx, m, k, rp, ci, v)
+    r = subprocess.run([MINIMPIRUN, "-np", "4", exe, mtx, "32", "2", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    mobj = re.search(r"\|\|C_ref - C\|\|_f / \|\|C_ref\|\|_f = ([0-9.eE+-]+)", r.stdout)
+    assert mobj and float(mobj.group(1)) <= 1e-12, r.stdout
