@@ -12,7 +12,7 @@ import scipy.sparse as sp
 
 import oracle_lib as O
 from pycrp import gen
-from util import MINIMPIRUN, PKG
+from util import MINIMPIRUN, PKG, run_cmd
 
 UNVERIFIED = "written after the round-1 GPU budget was spent: the device path of the composite has not run on a GPU yet"
 
@@ -22,8 +22,7 @@ def run(tmp_path, csr, n, nproc, *extra, plan_only=False, timeout=180):
     env = dict(os.environ, PYTHONPATH=PKG, OMP_NUM_THREADS="2")
     if plan_only:
         env["CRP_SPMM_PLAN_ONLY"] = "1"
-    r = subprocess.run([MINIMPIRUN, "-np", str(nproc), sys.executable, "-m", "pycrp.composite_flow", csr, str(n), prefix, *extra],
-                       capture_output=True, text=True, env=env, timeout=timeout)
+    r = run_cmd([MINIMPIRUN, "-np", str(nproc), sys.executable, "-m", "pycrp.composite_flow", csr, str(n), prefix, *extra], env=env, timeout=timeout)
     assert r.returncode == 0, r.stdout + r.stderr
     return [dict(np.load(f"{prefix}.r{i}.npz")) for i in range(nproc)], r.stdout
 
@@ -78,7 +77,7 @@ def test_deprecated_driver_runs_unchanged(tmp_path):
     m, k, rp, ci, v = gen.pwtk_like(m=1500, target_nnz=77000, bandwidth=1200, grid_w=10, seed=5)
     mtx = os.path.join(str(tmp_path), "small.mtx")
     gen.write_mtx(mtx, m, k, rp, ci, v)
-    r = subprocess.run([MINIMPIRUN, "-np", "4", exe, mtx, "32", "2", "1"], capture_output=True, text=True, timeout=180)
+    r = run_cmd([MINIMPIRUN, "-np", "4", exe, mtx, "32", "2", "1"], timeout=180)
     assert r.returncode == 0, r.stdout + r.stderr
     mobj = re.search(r"\|\|C_ref - C\|\|_f / \|\|C_ref\|\|_f = ([0-9.eE+-]+)", r.stdout)
     assert mobj and float(mobj.group(1)) <= 1e-12, r.stdout

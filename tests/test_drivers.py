@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from pycrp import gen
-from util import MINIMPIRUN, PKG
+from util import MINIMPIRUN, PKG, run_cmd
 
 BIN = os.path.join(PKG, "bin")
 ROOT = os.path.dirname(PKG)
@@ -33,7 +33,7 @@ def test_reference_driver_runs_unchanged(exe, nproc, n, tmp_path):
     if not have(exe):
         pytest.skip("drivers not built (needs the reference sources at build time)")
     mtx = write_mtx(tmp_path)
-    r = subprocess.run([MINIMPIRUN, "-np", str(nproc), os.path.join(BIN, exe), mtx, str(n), "3", "0", "1"], capture_output=True, text=True, timeout=600)
+    r = run_cmd([MINIMPIRUN, "-np", str(nproc), os.path.join(BIN, exe), mtx, str(n), "3", "0", "1"], timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     mobj = re.search(r"\|\|C_ref - C\|\|_f / \|\|C_ref\|\|_f = ([0-9.eE+-]+)", r.stdout)
     assert mobj, r.stdout

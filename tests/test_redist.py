@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import cases
-from util import MINIMPIRUN, PKG
+from util import MINIMPIRUN, PKG, run_cmd
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PLAN_KEYS = ("n_proc_send", "n_proc_recv", "send_cnt", "recv_cnt", "send_ranks", "send_sizes", "send_displs", "sblk_sizes",
@@ -26,7 +26,7 @@ def run_redist(tmp_path, name, extra=()):
     prefix = os.path.join(str(tmp_path), "rd")
     env = dict(os.environ, PYTHONPATH=PKG)
     cmd = [MINIMPIRUN, "-np", str(len(lay)), sys.executable, "-m", "pycrp.redist_flow", path, prefix, *extra]
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    r = run_cmd(cmd, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     return [dict(np.load(f"{prefix}.r{i}.npz")) for i in range(len(lay))]
 

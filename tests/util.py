@@ -10,6 +10,27 @@ PKG = os.path.join(ROOT, "crp-spmm_b200")
 MINIMPIRUN = os.path.join(PKG, "bin", "minimpirun")
 
 
+class Result:
+    def __init__(self, returncode, stdout, stderr):
+        self.returncode, self.stdout, self.stderr = returncode, stdout, stderr
+
+
+def run_cmd(cmd, env=None, timeout=600):
+    """subprocess.run that, on timeout, kills the whole process group (mini-MPI ranks included) instead of leaving orphans on the GPU."""
+    import signal
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        out, err = p.communicate()
+        return Result(-9, out, err + f"\n[timeout after {timeout} s: process group killed]")
+    return Result(p.returncode, out, err)
+
+
 def run_flow(tmp_path, csr_path, n, mode, nproc, layout=0, reidx=1, plan_only=False, device=False, f32=False, extra_env=None, timeout=600):
     """python -m pycrp.flow on `nproc` ranks; returns the list of per-rank dump dicts."""
     prefix = os.path.join(str(tmp_path), "dump")
@@ -27,7 +48,7 @@ def run_flow(tmp_path, csr_path, n, mode, nproc, layout=0, reidx=1, plan_only=Fa
         cmd.append("--device")
     if f32:
         cmd.append("--f32")
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
+    r = run_cmd(cmd, env=env, timeout=timeout)
     assert r.returncode == 0, f"{' '.join(cmd)}\nstdout:\n{r.stdout}\nstderr:\n{r.stderr}"
     return [dict(np.load(f"{prefix}.r{i}.npz")) for i in range(nproc)]
 
