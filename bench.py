@@ -115,7 +115,7 @@ def measured_traffic(workload, kernel):
         return None
 
 
-def run_reference_cpu(csr, n, mode, steps, nranks=4):
+def run_reference_cpu(csr, n, mode, steps, nranks=4, warmup=1):
     """The reference sources under oracle/_ref on the host cores: returns (gflops, seconds per exec, cores, sample)."""
     ref = os.path.join(ROOT, "oracle", "_ref")
     exe, run = os.path.join(ref, "ref_dump.exe"), os.path.join(ref, "minimpirun")
@@ -127,7 +127,7 @@ def run_reference_cpu(csr, n, mode, steps, nranks=4):
     env = dict(os.environ, OMP_NUM_THREADS=str(thr), OMP_PLACES="cores", OMP_PROC_BIND="close")
     for k_ in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT", "MASTER_ADDR", "TORCHELASTIC_RUN_ID", "MINIMPI_DIR", "MINIMPI_RANK", "MINIMPI_SIZE"):
         env.pop(k_, None)
-    out = subprocess.run([run, "-np", str(nranks), exe, csr, str(n), str(steps), mode, "-"], capture_output=True, text=True, env=env, timeout=1500)
+    out = subprocess.run([run, "-np", str(nranks), exe, csr, str(n), str(steps), mode, "-", "0", str(warmup)], capture_output=True, text=True, env=env, timeout=1500)
     if out.returncode != 0:
         raise RuntimeError("reference CPU run failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
     mobj = re.search(r"REFDUMP exec_s min ([\d.eE+-]+) avg ([\d.eE+-]+) max ([\d.eE+-]+) local_spmm_max_s ([\d.eE+-]+)", out.stdout)
@@ -135,7 +135,7 @@ def run_reference_cpu(csr, n, mode, steps, nranks=4):
     avg = float(mobj.group(2))
     nnz = int(g.group(3))
     return {"gflops": 2.0 * nnz * n / avg / 1e9, "sec": avg, "cores": nranks * thr, "ranks": nranks, "threads": thr,
-            "grid": f"{g.group(1)}x{g.group(2)}", "local_spmm_s": float(mobj.group(4)), "steps": steps}
+            "grid": f"{g.group(1)}x{g.group(2)}", "local_spmm_s": float(mobj.group(4)), "steps": steps, "warmup": warmup}
 
 
 def main():
@@ -161,13 +161,13 @@ def main():
         if rank_env != 0:
             return 0
         csr = matrix_path(a.workload)
-        steps = max(1, min(a.steps, 5))
-        r = run_reference_cpu(csr, n, mode, steps, nranks=4)
+        steps = max(1, min(a.steps, 100))        # one exec of the whole workload is ~0.3 s on the host cores: K steps stay within minutes
+        r = run_reference_cpu(csr, n, mode, steps, nranks=4, warmup=max(1, min(a.warmup, 10)))
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) is missing"}))
             return 0
-        sample = f"whole workload, {r['steps']} timed execs after 1 warm-up, {r['ranks']} ranks x {r['threads']} OpenMP threads, grid {r['grid']}"
-        line = {"impl": "reference", "metric": METRIC, "value": r["gflops"], "unit": "GFLOP/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": 1,
+        sample = f"whole workload, {r['steps']} timed execs after {r['warmup']} warm-up, {r['ranks']} ranks x {r['threads']} OpenMP threads, grid {r['grid']}"
+        line = {"impl": "reference", "metric": METRIC, "value": r["gflops"], "unit": "GFLOP/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": r["warmup"],
                 "ms_per_step": 1e3 * r["sec"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_s, "data": "synthetic",
                 "config": {"workload": desc, "n": n, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow"},
                 "cpu_baseline": {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["cores"], "kind": "reference", "sample": sample,

@@ -11,7 +11,7 @@
  *   mode "rp": examples/test_rp_spmm.c:41-145
  * but reads a binary CSR (every rank reads its own slice) instead of a .mtx.
  *
- * usage: minimpirun -np P ref_dump <csr.bin> <n> <ntest> <2d|rp> <dump-prefix|-> [layout]
+ * usage: minimpirun -np P ref_dump <csr.bin> <n> <ntest> <2d|rp> <dump-prefix|-> [layout] [warmup]
  *
  * Binary CSR: "CRPCSR1\0", int64 m, k, nnz, int32 rowptr[m+1], int32 colidx[nnz], f64 val[nnz].
  * Dump file <prefix>.r<rank>.bin: a sequence of records
@@ -90,6 +90,8 @@ int main(int argc, char **argv)
     int mode2d = (strcmp(argv[4], "2d") == 0);
     const char *prefix = argv[5];
     int layout = (argc >= 7) ? atoi(argv[6]) : 0;
+    int n_warm = (argc >= 8) ? atoi(argv[7]) : 1;      /* the reference drivers do one untimed exec */
+    if (n_warm < 1) n_warm = 1;
 
     int nproc, rank;
     MPI_Init(&argc, &argv);
@@ -197,7 +199,7 @@ int main(int argc, char **argv)
     }
 
     /* warm-up + timed loop (test_para2d_spmm.c:151-165) */
-    rp_spmm_exec(rp, layout, B, ldB, C, ldC);
+    for (int it = 0; it < n_warm; it++) rp_spmm_exec(rp, layout, B, ldB, C, ldC);
     rp_spmm_clear_stat(rp);
     double t_sum = 0.0, t_min = 1e30, t_max = 0.0;
     for (int it = 0; it < n_test; it++)
