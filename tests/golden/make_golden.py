@@ -41,7 +41,7 @@ def main():
             gen.write_csr_bin(csr, m, k, rp, ci, v)
             prefix = os.path.join(tmp, name)
             out = run([os.path.join(REF, "minimpirun"), "-np", str(nproc), "-x", f"RP_SPMM_REIDX={reidx}", "-x", "OMP_NUM_THREADS=1",
-                       os.path.join(REF, "ref_dump.exe"), csr, str(n), "0", mode, prefix, str(layout)])
+                       os.path.join(REF, "ref_dump.exe"), csr, str(n), "1", mode, prefix, str(layout)])     # 1 timed exec: the stat table is printed
             rec = dict(m=m, k=k, n=n, nproc=nproc, layout=layout, reidx=reidx, mode=np.array(mode),
                        csr_rowptr=rp, csr_colidx=ci, csr_val=v, stdout=np.array(out))
             for r in range(nproc):
