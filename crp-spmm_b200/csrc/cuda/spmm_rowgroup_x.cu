@@ -1,6 +1,6 @@
 // spmm_rowgroup_x.cu - EXPERIMENTAL lean variants of the row-group kernel (fp64, 128-bit, full column chunks only).
 //
-// NOT on the default path: reached only through the development switch CRP_SPMM_RG_CFG = 60..63
+// NOT on the default path: reached only through the development switch CRP_SPMM_RG_CFG = 60..64
 // (spmm_rowgroup.cu, rg_launch_experiment).  Written at the end of round 1, after the GPU budget was spent, from the
 // SASS of the shipped kernel (spmm_rowgroup_sv_kernel<double,2,6,4,2,128,32>): its hot loop issues 203 instructions per
 // 96 DFMA - 16 CS2R (zero fill for column groups beyond n), 11 ISETP / 4 SEL / 4 BRA (bounds and X0 / X1 selection),
@@ -152,6 +152,139 @@ __global__ void __launch_bounds__(BS, (BS == 128 ? 3 : 1)) spmm_rowgroup_x_kerne
     }
 }
 
+// Two warps per group ("split-2"): each takes one half of the group's blocks, the second warp hands its partial sums over
+// through shared memory and the first adds them (first half + second half: a fixed order, but not the row-split kernel's
+// left-to-right order - results agree to rounding, not bit for bit).  Meant for small per-rank problems (8 GPUs: 4540
+// groups on 1776 resident warps = 2.6 waves of 27-step dependency chains): twice the warps, half the chain length.
+template <int R, int U, int NB, int CB>
+__global__ void __launch_bounds__(128, 3) spmm_rowgroup_x2_kernel(
+    const int ngroups, const int *__restrict__ grow, const int *__restrict__ gptr,
+    const int *__restrict__ bcol, const double *__restrict__ bval,
+    const double2 *__restrict__ X, const size_t ldx2, const double alpha, double2 *__restrict__ C, const size_t ldc2
+)
+{
+    static_assert(R % 2 == 0 && CB % NB == 0, "layout assumptions");
+    __shared__ __align__(16) double s_val[4][2][CB * R];
+    __shared__ int s_col[4][2][CB];
+    __shared__ double2 s_part[2][R][U][32];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = wib >> 1, half = wib & 1;
+    const int g = blockIdx.x * 2 + pair;
+    const bool valid = g < ngroups;
+    const double2 *xlane = X + (size_t) blockIdx.y * (32 * U) + lane;
+    double2 *clane = C + (size_t) blockIdx.y * (32 * U) + lane;
+    int p_beg = 0, p_end = 0, row0 = 0;
+    if (valid)
+    {
+        const int b = __ldg(gptr + g), e = __ldg(gptr + g + 1);
+        row0 = __ldg(grow + g);
+        int mid = b + (((e - b) / 2 + NB - 1) / NB) * NB;          // first half: a multiple of NB blocks
+        if (mid > e) mid = e;
+        p_beg = half ? mid : b;
+        p_end = half ? e : mid;
+    }
+    double2 acc[R][U];
+    #pragma unroll
+    for (int r = 0; r < R; r++)
+        #pragma unroll
+        for (int u = 0; u < U; u++) acc[r][u] = make_double2(0.0, 0.0);
+
+    auto stage = [&](const int buf, const int pc, const int nb) {
+        const char *src = (const char *) (bval + (size_t) pc * R);
+        const int nbytes = nb * R * 8;
+        for (int off = lane * 16; off < nbytes; off += 32 * 16) cpa16((char *) &s_val[wib][buf][0] + off, src + off);
+        for (int j = lane; j < nb; j += 32) cpa4(&s_col[wib][buf][j], bcol + pc + j);
+        cpa_commit();
+    };
+    int buf = 0;
+    if (p_beg < p_end) stage(0, p_beg, min(CB, p_end - p_beg));
+    for (int pc = p_beg; pc < p_end; pc += CB, buf ^= 1)
+    {
+        const int nb = min(CB, p_end - pc);
+        cpa_wait_all();
+        __syncwarp();
+        if (pc + CB < p_end) stage(buf ^ 1, pc + CB, min(CB, p_end - pc - CB));
+        const double *sv = &s_val[wib][buf][0];
+        const int *sc = &s_col[wib][buf][0];
+        int j = 0;
+        for (; j + NB <= nb; j += NB)
+        {
+            double2 x[NB][U];
+            #pragma unroll
+            for (int q = 0; q < NB; q++)
+            {
+                const double2 *xr = xlane + (size_t) sc[j + q] * ldx2;
+                #pragma unroll
+                for (int u = 0; u < U; u++) x[q][u] = __ldg(xr + u * 32);
+            }
+            #pragma unroll
+            for (int q = 0; q < NB; q++)
+            {
+                double a[R];
+                #pragma unroll
+                for (int i = 0; i < R / 2; i++)
+                {
+                    const double2 t = reinterpret_cast<const double2 *>(sv + (size_t) (j + q) * R)[i];
+                    a[2 * i] = t.x; a[2 * i + 1] = t.y;
+                }
+                #pragma unroll
+                for (int r = 0; r < R; r++)
+                    #pragma unroll
+                    for (int u = 0; u < U; u++)
+                    {
+                        acc[r][u].x = fma(a[r], x[q][u].x, acc[r][u].x);
+                        acc[r][u].y = fma(a[r], x[q][u].y, acc[r][u].y);
+                    }
+            }
+        }
+        for (; j < nb; j++)
+        {
+            const double2 *xr = xlane + (size_t) sc[j] * ldx2;
+            double a[R];
+            #pragma unroll
+            for (int i = 0; i < R / 2; i++)
+            {
+                const double2 t = reinterpret_cast<const double2 *>(sv + (size_t) j * R)[i];
+                a[2 * i] = t.x; a[2 * i + 1] = t.y;
+            }
+            #pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                const double2 xx = __ldg(xr + u * 32);
+                #pragma unroll
+                for (int r = 0; r < R; r++)
+                {
+                    acc[r][u].x = fma(a[r], xx.x, acc[r][u].x);
+                    acc[r][u].y = fma(a[r], xx.y, acc[r][u].y);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (half == 1)
+    {
+        #pragma unroll
+        for (int r = 0; r < R; r++)
+            #pragma unroll
+            for (int u = 0; u < U; u++) s_part[pair][r][u][lane] = acc[r][u];
+    }
+    __syncthreads();                                // every thread of the CTA gets here (no early return above)
+    if (half == 0 && valid)
+    {
+        #pragma unroll
+        for (int r = 0; r < R; r++)
+        {
+            double2 *crow = clane + (size_t) (row0 + r) * ldc2;
+            #pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                const double2 o = s_part[pair][r][u][lane];
+                __stcs(crow + u * 32, make_double2(alpha * (acc[r][u].x + o.x), alpha * (acc[r][u].y + o.y)));
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // returns false when the launch conditions of the lean variants do not hold (caller falls back to the shipped kernel)
@@ -178,6 +311,10 @@ bool crp_launch_rowgroup_x(
         case 61: CRP_X(2, 128, 32, true, resident); break;
         case 62: CRP_X(1, 128, 32, true, resident); break;
         case 63: CRP_X(2, 128, 64, true, resident); break;
+        case 64:
+            spmm_rowgroup_x2_kernel<6, 4, 2, 32><<<dim3((unsigned) ((rg->ngroups + 1) / 2), chunks), 128, 0, s>>>(
+                rg->ngroups, rg->d_grow, rg->d_gptr, rg->d_bcol, bval, (const double2 *) X0, ldx0 / 2, alpha, (double2 *) C, ldc / 2);
+            break;
         default: return false;
     }
 #undef CRP_X
