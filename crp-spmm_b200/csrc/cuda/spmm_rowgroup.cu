@@ -733,7 +733,9 @@ bool crp_launch_rowgroup_x(
     const double *X1, const double alpha, const double beta, double *C, const size_t ldc, cudaStream_t s
 );
 
-// development sweep (CRP_SPMM_RG_CFG = index): fp64, 128-bit, R = 6, full-warp groups only
+// development switch (CRP_SPMM_RG_CFG = index): fp64, 128-bit, R = 6, full-warp groups only.
+// Indices 0..49 are the configurations measured in round 1 (compiled only with -DCRP_DEV_SWEEP); 60.. are the lean variants of
+// spmm_rowgroup_x.cu.  Without the variable, or for an index that is not compiled in, the shipped kernel runs.
 template <typename T, int VEC, int R>
 static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
 {
@@ -742,6 +744,7 @@ static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, 
         const char *e = getenv("CRP_SPMM_RG_CFG");
         if (e == NULL || nv < 128) return false;
         if (atoi(e) >= 60) return crp_launch_rowgroup_x(atoi(e), rg, bval, nv * VEC, X0, ldx0, X1, alpha, 0.0, C, ldc, s);   // spmm_rowgroup_x.cu
+#ifdef CRP_DEV_SWEEP     /* the round-1 sweep (profiles/kbench*.log): build with CRP_NVCC_EXTRA=-DCRP_DEV_SWEEP to get these ~40 instantiations */
 #define CRP_RGX(U, NB, PIPE, PF, BS) rg_launch_one<T, VEC, R, 32, U, NB, PIPE, PF, BS>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s); return true
         switch (atoi(e))
         {
@@ -798,6 +801,7 @@ static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, 
             default: return false;
         }
 #undef CRP_RGX
+#endif
     }
     return false;
 }

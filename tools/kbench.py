@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Kernel-only timing of the local SpMM variants on one GPU (development aid; bench.py is the contract).
    python tools/kbench.py [--workload pwtk] [--n 256] [--variants auto,rowsplit] [--iters 10] [--env K=V,...]
-Each variant is timed with CUDA events around single launches, L2 flushed in between."""
+Each variant is timed with CUDA events around single launches, L2 flushed in between.
+Variant specs may carry environment settings, e.g. auto:CRP_SPMM_RG_CFG=61 (indices 0..49 need a library built with
+CRP_NVCC_EXTRA=-DCRP_DEV_SWEEP; 60..64 are always available)."""
 import argparse
 import json
 import os
