@@ -69,6 +69,30 @@ void dev_type_free(void *mem, dev_type_t dev_type)
     }
 }
 
+int dev_type_alloc_workbufs(dev_type_t dev_type, size_t bytes, void **workbuf_h, void **workbuf_d)
+{
+    *workbuf_h = NULL;
+    *workbuf_d = NULL;
+    const int want_h = (dev_type == DEV_TYPE_HOST) || (dev_type == DEV_TYPE_CUDA);
+    const int want_d = is_cuda_type(dev_type);
+    if (want_h)
+    {
+        *workbuf_h = dev_type_malloc(bytes, DEV_TYPE_HOST);
+        if (*workbuf_h == NULL && bytes > 0) return 1;
+    }
+    if (want_d)
+    {
+        *workbuf_d = dev_type_malloc(bytes, DEV_TYPE_CUDA);
+        if (*workbuf_d == NULL && bytes > 0)
+        {
+            if (*workbuf_h != NULL) dev_type_free(*workbuf_h, DEV_TYPE_HOST);
+            *workbuf_h = NULL;
+            return 2;
+        }
+    }
+    return 0;
+}
+
 void dev_type_realloc(size_t *curr_bytes, size_t req_bytes, dev_type_t dev_type, void **mem)
 {
     if (req_bytes <= *curr_bytes) return;

@@ -60,34 +60,28 @@ void dev_type_copy_matrix(
 }
 #endif
 
-/* Allocate the host and/or device work buffer an engine asked for and attach it. */
-#define MALLOC_ATTACH_WORKBUF(attach_func, free_func, engine, dev_type, workbuf_bytes, workbuf_h, workbuf_d) \
-    do {                                                                                \
-        int crp_need_h_ = ((dev_type) == DEV_TYPE_HOST) || ((dev_type) == DEV_TYPE_CUDA);               \
-        int crp_need_d_ = ((dev_type) == DEV_TYPE_CUDA) || ((dev_type) == DEV_TYPE_CUDA_MPI_DIRECT);    \
-        workbuf_h = NULL;                                                               \
-        workbuf_d = NULL;                                                               \
-        if (crp_need_h_)                                                                \
-        {                                                                               \
-            workbuf_h = dev_type_malloc(workbuf_bytes, DEV_TYPE_HOST);                  \
-            if (workbuf_h == NULL)                                                      \
-            {                                                                           \
-                ERROR_PRINTF("Allocate host workbuf failed\n");                         \
-                free_func(&engine);                                                     \
-                break;                                                                  \
-            }                                                                           \
-        }                                                                               \
-        if (crp_need_d_)                                                                \
-        {                                                                               \
-            workbuf_d = dev_type_malloc(workbuf_bytes, DEV_TYPE_CUDA);                  \
-            if (workbuf_d == NULL)                                                      \
-            {                                                                           \
-                ERROR_PRINTF("Allocate CUDA workbuf failed\n");                         \
-                free_func(&engine);                                                     \
-                break;                                                                  \
-            }                                                                           \
-        }                                                                               \
-        attach_func(engine, workbuf_h, workbuf_d);                                      \
+/* Host and / or device work buffer for an engine of the given memory space: DEV_TYPE_HOST wants a host buffer,
+ * DEV_TYPE_CUDA both (host mirror + device), DEV_TYPE_CUDA_MPI_DIRECT a device buffer only.
+ * Returns 0 on success, 1 if the host allocation failed, 2 if the device allocation failed (nothing stays allocated). */
+#ifdef __cplusplus
+extern "C"
+#endif
+int dev_type_alloc_workbufs(dev_type_t dev_type, size_t bytes, void **workbuf_h, void **workbuf_d);
+
+/* Same contract as the reference's macro of this name (src/dev_type.h:63-88): allocate what `dev_type` needs, hand it to
+ * attach_func(engine, host, device); on failure report, release the engine with free_func(&engine) and attach nothing. */
+#define MALLOC_ATTACH_WORKBUF(attach_func, free_func, engine, dev_type, workbuf_bytes, workbuf_h, workbuf_d)              \
+    do {                                                                                                                  \
+        void *crp_wb_h_ = NULL, *crp_wb_d_ = NULL;                                                                        \
+        const int crp_wb_rc_ = dev_type_alloc_workbufs((dev_type), (workbuf_bytes), &crp_wb_h_, &crp_wb_d_);              \
+        workbuf_h = crp_wb_h_;                                                                                            \
+        workbuf_d = crp_wb_d_;                                                                                            \
+        if (crp_wb_rc_ == 0) attach_func(engine, workbuf_h, workbuf_d);                                                   \
+        else                                                                                                              \
+        {                                                                                                                 \
+            ERROR_PRINTF("Allocate %s workbuf failed\n", crp_wb_rc_ == 1 ? "host" : "CUDA");                              \
+            free_func(&engine);                                                                                           \
+        }                                                                                                                 \
     } while (0)
 
 #endif
