@@ -73,6 +73,43 @@ static double analyse_R(const int m, const int *rowptr, const rg_rowinfo &ri, co
     return (double) nblk * (4.0 + R) + (double) rest * 5.0;
 }
 
+// the group size and alignment with the lowest modelled cost (R = 1: keep the row-split kernel); forced: CRP_SPMM_ROWGROUP_R
+static void rg_choose(const int m, const int *rowptr, const rg_rowinfo &ri, const int forced, int *best_R_, int *best_off_, long long *nblk_)
+{
+    double best_cost = (double) rowptr[m] * 5.0;      // everything in the row-split kernel
+    int best_R = 1, best_off = 0;
+    long long best_nblk = 0;
+    for (int R : kCandR)
+    {
+        if (forced > 1 && R != forced) continue;
+        for (int off = 0; off < R && off < m; off++)
+        {
+            long long nblk, rest;
+            const double cost = analyse_R(m, rowptr, ri, R, off, &nblk, &rest);
+            const bool take = (forced > 1) ? (nblk > 0 && (best_R == 1 || cost < best_cost)) : (cost < 0.9 * best_cost || (best_R == R && cost < best_cost));
+            if (take) { best_cost = cost; best_R = R; best_off = off; best_nblk = nblk; }
+        }
+    }
+    *best_R_ = best_R;  *best_off_ = best_off;  *nblk_ = best_nblk;
+}
+
+// Host-only view of the plan-time decision (no device needed): which group size / alignment would be used for this CSR
+// pattern and how many R x 1 blocks it yields.  R = 1 means "row-split kernel only".
+extern "C" void crp_cuda_spmm_analyse(const int m, const int *rowptr, const int *colidx, int *R, int *offset, long long *nblk, int *n_long_rows)
+{
+    *R = 1;  *offset = 0;  *nblk = 0;  *n_long_rows = 0;
+    if (m <= 0 || rowptr[m] == rowptr[0]) return;
+    int forced = 0;
+    if (const char *e = getenv("CRP_SPMM_ROWGROUP_R")) forced = atoi(e);
+    if (forced != 1)
+    {
+        rg_rowinfo ri;
+        rg_scan_rows(m, rowptr, colidx, &ri);
+        rg_choose(m, rowptr, ri, forced, R, offset, nblk);
+    }
+    for (int i = 0; i < m; i++) if (rowptr[i + 1] - rowptr[i] > CRP_LONG_ROW) (*n_long_rows)++;
+}
+
 void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val, std::vector<int> *rest_out)
 {
     if (rest_out) rest_out->clear();
@@ -85,19 +122,9 @@ void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colid
     if (forced == 1) return;
     rg_rowinfo ri;
     rg_scan_rows(m, rowptr, colidx, &ri);
-    double best_cost = (double) plan->nnz * 5.0;      // everything in the row-split kernel
     int best_R = 1, best_off = 0;
-    for (int R : kCandR)
-    {
-        if (forced > 1 && R != forced) continue;
-        for (int off = 0; off < R && off < m; off++)
-        {
-            long long nblk, rest;
-            const double cost = analyse_R(m, rowptr, ri, R, off, &nblk, &rest);
-            const bool take = (forced > 1) ? (nblk > 0 && (best_R == 1 || cost < best_cost)) : (cost < 0.9 * best_cost || (best_R == R && cost < best_cost));
-            if (take) { best_cost = cost; best_R = R; best_off = off; }
-        }
-    }
+    long long best_nblk = 0;
+    rg_choose(m, rowptr, ri, forced, &best_R, &best_off, &best_nblk);
     if (best_R == 1) return;
 
     const int R = best_R;

@@ -200,6 +200,7 @@ def load():
     L.crp_cuda_spmm_plan_create.argtypes = [i, i, i, vp, vp, vp, i]
     L.crp_cuda_spmm_plan_create.restype = vp
     L.crp_cuda_spmm_plan_destroy.argtypes = [vp]
+    L.crp_cuda_spmm_analyse.argtypes = [i, vp, vp, c_int_p, c_int_p, C.POINTER(C.c_longlong), c_int_p]
     L.crp_cuda_spmm_exec.argtypes = [vp, i, i, d, vp, i, vp, i, d, vp, i, vp]
     L.crp_cuda_spmm_last_kernel.argtypes = [vp]
     L.crp_cuda_spmm_last_kernel.restype = C.c_char_p

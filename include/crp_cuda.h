@@ -131,6 +131,10 @@ const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan);
 /* force a kernel variant for experiments: "auto", "rowsplit", "rowgroup", "mergepath" */
 void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name);
 
+/* Host-only view of the plan-time kernel selection (needs no device): the row-group size R (1 = row-split kernel only), the
+ * alignment of the first group, the number of R x 1 blocks, and how many rows are long enough to be cut into segments. */
+void crp_cuda_spmm_analyse(const int m, const int *rowptr, const int *colidx, int *R, int *offset, long long *nblk, int *n_long_rows);
+
 /* Host-in / host-out convenience with the deprecated proxy's argument list:
  * C_h := alpha * A * B_h + beta * C_h, everything on the host, row-major fp64. */
 void crp_cuda_csr_spmm_host(
