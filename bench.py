@@ -106,13 +106,46 @@ def measured_peak_hbm():
 
 
 def measured_traffic(workload, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this kernel, or None."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch, source) from the ncu capture of this kernel on this workload
+    (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py from an `ncu --set full` run of bench.py), or (None, why)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             e = json.load(f).get(f"{workload}:{kernel}")
-        return None if e is None else e["dram_read_bytes"] + e["dram_write_bytes"]
-    except Exception:
-        return None
+        if e is None:
+            return None, "no ncu capture of this kernel on this workload in profiles/r02_ncu_traffic.json"
+        return e["dram_read_bytes"] + e["dram_write_bytes"], e.get("source", "profiles/r02_ncu_traffic.json")
+    except Exception as exc:
+        return None, f"profiles/r02_ncu_traffic.json unreadable: {exc}"[:200]
+
+
+def sampled_parity(pb, C_dev, nsample=4096, seed=1234):
+    """||C - C_ref||_F / ||C_ref||_F on `nsample` rows of this rank's C block, C_ref = the plain CSR product in fp64
+    (scipy.sparse on the rows' nonzeros; B is the drivers' analytic fill, evaluated only on the rows that are referenced).
+    Returns (sum of squared differences, sum of squared reference entries, rows checked)."""
+    import scipy.sparse as sp
+    from pycrp import gen
+    nrow = pb.c_nrow
+    if nrow == 0 or pb.bc_ncol == 0:
+        return 0.0, 0.0, 0
+    rng = np.random.default_rng(seed + pb.rank)
+    loc = np.sort(rng.choice(nrow, size=min(nsample, nrow), replace=False))
+    m, k, rowptr, colidx, val = gen.read_csr_bin(pb.csr_path, mmap=True)
+    rows = loc + pb.c_srow
+    lens = (rowptr[rows + 1] - rowptr[rows]).astype(np.int64)
+    idx = np.concatenate([np.arange(rowptr[r], rowptr[r + 1], dtype=np.int64) for r in rows]) if lens.sum() else np.zeros(0, np.int64)
+    cols = np.asarray(colidx[idx], dtype=np.int64)
+    vals = np.asarray(val[idx], dtype=np.float64)
+    if pb.dtype == np.float32:
+        vals = vals.astype(np.float32).astype(np.float64)          # the fp32 engine rounds A once
+    ucols, inv = np.unique(cols, return_inverse=True)
+    Bu = (np.asarray(ucols, np.float64)[:, None] * 0.19 + np.arange(pb.bc_scol, pb.bc_scol + pb.bc_ncol, dtype=np.float64)[None, :] * 0.24)
+    Bu = Bu.astype(pb.dtype).astype(np.float64)
+    indptr = np.zeros(rows.size + 1, np.int64)
+    indptr[1:] = np.cumsum(lens)
+    A = sp.csr_matrix((vals, inv, indptr), shape=(rows.size, max(ucols.size, 1)))
+    Cref = A @ Bu if ucols.size else np.zeros((rows.size, pb.bc_ncol))
+    Cs = C_dev[loc].astype(np.float64)
+    return float(np.sum((Cs - Cref) ** 2)), float(np.sum(Cref ** 2)), int(rows.size)
 
 
 def run_reference_cpu(csr, n, mode, steps, nranks=4, warmup=1):
@@ -177,7 +210,11 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm (B200)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    if world_env > 1:
+        # NCCL's INIT lines (rank / nranks of every communicator) go to stderr: rank 0 prints exactly one JSON line on stdout
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     from pycrp import capi
     from pycrp.flow import Problem
     L = capi.load()
@@ -190,7 +227,11 @@ def main():
     capi.mpi_barrier()
     csr = matrix_path(a.workload)
     dtype = np.float32 if dtype_s == "f32" else np.float64
+    nccl = None
+    if nproc > 1:
+        nccl = {"world_nranks": int(L.crp_nccl_world_nranks()), "version": int(L.crp_nccl_version())}
     pb = Problem(csr, n, mode, 0, dtype, rank, nproc).init()
+    pb.csr_path = csr
     if a.kernel != "auto":
         L.rp_spmm_set_kernel(pb.rp, a.kernel.encode())
     nnz, flops_total = pb.nnz, 2.0 * pb.nnz * n
@@ -239,12 +280,17 @@ def main():
     host_ms_per_step = 1e3 * (t1 - t0) / a.steps
     value = flops_total / (ms_per_step * 1e-3) / 1e9
 
-    # roofline of the local-SpMM kernel, from the engine's own CUDA events around it (same timed region)
+    # roofline of the local-SpMM kernel(s), from the engine's own CUDA events around them in the same timed region;
+    # rp_spmm_sync_stats folds the events of EVERY exec (the counters lag behind n_exec in non-blocking mode)
+    L.rp_spmm_sync_stats(pb.rp)
     r = pb.rp.contents
-    t_spmm = r.t_spmm / max(r.n_exec, 1)
-    t_pack, t_a2a = r.t_pack / max(r.n_exec, 1), r.t_a2a / max(r.n_exec, 1)
+    nx = max(int(r.n_exec), 1)                 # == a.steps: every timed exec is counted and folded
+    t_spmm = r.t_spmm / nx
+    t_pack, t_a2a = r.t_pack / nx, r.t_a2a / nx
     bytes_loc, flops_loc = pb.algorithmic_bytes()
     kern = L.rp_spmm_kernel_name(pb.rp).decode()
+    info = np.zeros(12, np.int64)
+    L.rp_spmm_plan_info(pb.rp, capi.ptr(info))
     t_spmm_max = capi.mpi_allreduce_max(t_spmm)
     t_spmm_min = -capi.mpi_allreduce_max(-t_spmm)
     bytes_sum = capi.mpi_allreduce_sum(float(bytes_loc))
@@ -255,10 +301,27 @@ def main():
     peak, peak_src = measured_peak_hbm()
     ach = bytes_loc / t_spmm / 1e9 if t_spmm > 0 else 0.0
     ach_job = bytes_sum / t_spmm_max / 1e9 / nproc if t_spmm_max > 0 else 0.0
+    dfma_peak = float(L.crp_cuda_measure_dfma_tflops()) if dtype_s == "f64" else None
 
-    # checksum of the device-resident result (parity of the timed run itself, see also tests/)
+    # per-rank table (rank 0 prints it): kernel ms, pack ms, exchange ms, rows, nnz, group size, grouped fraction, rest rows, received MB
+    nnz_loc = int(r.A_rowptr[r.A_nrow])
+    grouped = float(info[10] - info[4]) / max(float(info[10]), 1.0)
+    mine = np.array([1e3 * t_spmm, 1e3 * t_pack, 1e3 * t_a2a, r.A_nrow, nnz_loc, info[0], grouped, info[3], recv_bytes / 1e6, info[5], my_ms], dtype=np.float64)
+    allr = np.zeros((nproc, mine.size))
+    for q in range(nproc):
+        row = mine.copy() if q == rank else np.zeros_like(mine)
+        capi.mpi_bcast(row, q)
+        allr[q] = row
+
+    # parity of the timed run itself: relative F-norm error against the CSR loop on sampled rows of every rank's C block
     C_dev = dC.to_numpy(C_.shape, C_.dtype)
+    num, den, nrows_chk = sampled_parity(pb, C_dev)
+    rank_err = (num / den) ** 0.5 if den > 0 else 0.0
+    par_max = capi.mpi_allreduce_max(rank_err)
+    par_num, par_den = capi.mpi_allreduce_sum(num), capi.mpi_allreduce_sum(den)
+    par_rows = capi.mpi_allreduce_sum(float(nrows_chk))
     csum = capi.mpi_allreduce_sum(float(np.sum(C_dev.astype(np.float64))))
+    tol = 1e-12 if dtype_s == "f64" else 1e-5
 
     # ---- e2e: host B / C through the same public call ----
     e2e = None
@@ -302,20 +365,32 @@ def main():
             cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {exc}"[:300]}
 
     if rank == 0:
+        traffic, traffic_src = measured_traffic(a.workload, kern) if nproc == 1 else (None, "single-GPU captures only")
+        kernel_ms = 1e3 * (t_spmm if nproc == 1 else t_spmm_max)
+        kernel_tflops = flops_loc / t_spmm / 1e12 if t_spmm > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": nproc, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_s, "data": "synthetic",
-            "config": {"workload": desc, "n": n, "nnz": nnz, "grid": f"{pb.pm}x{pb.pn}", "comm_cost": pb.comm_cost,
+            "config": {"workload": desc, "n": n, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow"},
+            "detail": {"nnz": nnz, "grid": f"{pb.pm}x{pb.pn}", "comm_cost": pb.comm_cost, "kernel": kern,
                        "l2": "256 MiB memset between timed steps (outside the event pairs); B + C + A = %.0f MB per job" % (bytes_sum / 1e6),
-                       "kernel": kern, "driver": "test_para2d_spmm flow" if mode == "2d" else "test_rp_spmm flow", "checksum": csum,
-                       "ms_per_step_median": ms_median, "host_wall_ms_per_step_incl_flush": host_ms_per_step,
-                       "overlap": os.environ.get("CRP_SPMM_OVERLAP", "auto") if nproc > 1 else "n/a"},
+                       "checksum": csum, "ms_per_step_median": ms_median, "host_wall_ms_per_step_incl_flush": host_ms_per_step,
+                       "transport": os.environ.get("CRP_SPMM_TRANSPORT", "default (2: NVLink peer stores)") if nproc > 1 else "n/a",
+                       "overlap": os.environ.get("CRP_SPMM_OVERLAP", "auto") if nproc > 1 else "n/a", "nccl": nccl},
+            "parity": {"rel_err_max_over_ranks": par_max, "rel_err_all_ranks": (par_num / par_den) ** 0.5 if par_den > 0 else 0.0,
+                       "rows_checked": int(par_rows), "tol": tol, "ok": bool(par_max <= tol),
+                       "how": "||C - C_ref||_F / ||C_ref||_F on sampled rows of every rank's C block of the timed run; C_ref = fp64 CSR loop (scipy.sparse)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ach if nproc == 1 else ach_job, "peak": peak, "unit": "GB/s",
-                         "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": measured_traffic(a.workload, kern) if nproc == 1 else None, "peak_source": peak_src, "kernel": kern,
-                         "algorithmic_bytes_per_launch": bytes_loc if nproc == 1 else bytes_sum / nproc, "kernel_ms": 1e3 * (t_spmm if nproc == 1 else t_spmm_max),
-                         "kernel_gflops": flops_loc / t_spmm / 1e9 if t_spmm > 0 else 0.0},
+                         "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kern,
+                         "algorithmic_bytes_per_launch": bytes_loc if nproc == 1 else bytes_sum / nproc, "kernel_ms": kernel_ms,
+                         "kernel_ms_source": "CUDA events around the local-SpMM launches, folded over %d of %d timed execs (rp_spmm_sync_stats)" % (int(r.n_exec), a.steps),
+                         "kernel_share_of_step": kernel_ms / ms_per_step if ms_per_step > 0 else None,
+                         "fp64": None if dfma_peak is None else {"achieved_tflops": kernel_tflops, "peak_tflops": dfma_peak, "frac": kernel_tflops / dfma_peak,
+                                                                 "peak_source": "measured in this run: 8 independent DFMA chains per thread on all SMs"}},
             "phases_ms": {"pack": 1e3 * t_pack, "exchange": 1e3 * t_a2a_max, "local_spmm": 1e3 * t_spmm_max, "local_spmm_min_rank": 1e3 * t_spmm_min},
+            "per_rank": {"columns": ["spmm_ms", "pack_ms", "exchange_ms", "rows", "nnz", "R", "grouped_nnz_frac", "rest_rows", "recv_MB", "panel_tiles", "step_ms"],
+                         "rows": [[round(float(x), 4) for x in row] for row in allr]},
             "nvlink": None if nproc == 1 or t_comm_max <= 0 else {"recv_bytes_max": recv_max, "comm_ms": 1e3 * t_comm_max, "achieved_gbs": recv_max / t_comm_max / 1e9, "peak_gbs": 770.0,
                                                                     "frac": recv_max / t_comm_max / 1e9 / 770.0, "peak_source": "measured peer copy, B200_PROFILING.md",
                                                                     "note": "put + flag wait; dominated by latency and rank skew at this volume"},

@@ -134,6 +134,22 @@ crp_nccl_comm *crp_nccl_get(MPI_Comm comm)
     return c;
 }
 
+/* Creates (or finds) the NCCL communicator of MPI_COMM_WORLD and returns its size: every data-plane communicator
+ * (grid rows, grid columns, redistribution groups) is a subset of it.  bench.py calls this once per multi-GPU run
+ * so that the NCCL INIT lines of the log show all ranks. */
+int crp_nccl_world_nranks(void)
+{
+    return crp_nccl_get(MPI_COMM_WORLD)->size;
+}
+
+int crp_nccl_version(void)
+{
+    int v = 0;
+    load_nccl();
+    NCCL_CHECK(g_nccl.GetVersion(&v));
+    return v;
+}
+
 int crp_nccl_rank(const crp_nccl_comm *nc) { return nc->rank; }
 int crp_nccl_size(const crp_nccl_comm *nc) { return nc->size; }
 

@@ -450,3 +450,49 @@ extern "C" void crp_cuda_transpose(size_t dt_size, const int nrow, const int nco
     else { fprintf(stderr, "[FATAL] crp_cuda_transpose: dt_size must be 4 or 8\n"); abort(); }
     CRP_LAUNCH_CHECK();
 }
+
+// ------------------------------------------------------------- fp64 FMA peak (measurement aid)
+// SURVEY.md §8(d) asks for the fp64 roofline next to the HBM one because the headline configuration sits on the
+// ridge (5.8 flop / byte).  8 independent FMA chains per thread, 16 warps per scheduler: pure DFMA issue.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, const int iters, const double b, const double c)
+{
+    double a[8];
+    #pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = (double) (threadIdx.x + j);
+    for (int i = 0; i < iters; i++)
+    {
+        #pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = fma(a[j], b, c);
+    }
+    double sum = 0.0;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) sum += a[j];
+    out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+extern "C" double crp_cuda_measure_dfma_tflops(void)
+{
+    const int nsm = crp_cuda_sm_count(), blocks = nsm * 8, iters = 4096;
+    double *out = NULL;
+    CRP_CUDA_CHECK(cudaMalloc((void **) &out, sizeof(double) * (size_t) blocks * 256));
+    cudaEvent_t e0, e1;
+    CRP_CUDA_CHECK(cudaEventCreate(&e0));
+    CRP_CUDA_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++)
+    {
+        CRP_CUDA_CHECK(cudaEventRecord(e0, 0));
+        dfma_peak_kernel<<<blocks, 256>>>(out, iters, 0.999999, 1e-9);
+        CRP_LAUNCH_CHECK();
+        CRP_CUDA_CHECK(cudaEventRecord(e1, 0));
+        CRP_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CRP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CRP_CUDA_CHECK(cudaEventDestroy(e0));
+    CRP_CUDA_CHECK(cudaEventDestroy(e1));
+    CRP_CUDA_CHECK(cudaFree(out));
+    const double flops = 2.0 * 8.0 * (double) iters * 256.0 * (double) blocks;
+    return flops / ((double) best * 1e-3) / 1e12;
+}

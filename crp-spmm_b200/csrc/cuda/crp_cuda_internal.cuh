@@ -31,7 +31,7 @@ void crp_count_launch();
 static inline cudaStream_t as_stream(void *s) { return (cudaStream_t) s; }
 
 // ---- SpMM plan: device CSR + auxiliary structures of the kernel variants ----
-enum { CRP_VARIANT_AUTO = 0, CRP_VARIANT_ROWSPLIT = 1, CRP_VARIANT_ROWGROUP = 2, CRP_VARIANT_MERGEPATH = 3 };
+enum { CRP_VARIANT_AUTO = 0, CRP_VARIANT_ROWSPLIT = 1, CRP_VARIANT_ROWGROUP = 2, CRP_VARIANT_MERGEPATH = 3, CRP_VARIANT_PANEL = 4 };
 
 // Rows of the row-split kernel with more than CRP_LONG_ROW nonzeros are cut into segments of
 // CRP_LONG_SEG nonzeros that are multiplied as independent "virtual rows" into a scratch matrix and
@@ -55,6 +55,7 @@ struct crp_longrows
 struct crp_rowgroup
 {
     int       R;                // rows per group (0: not built / not worthwhile)
+    int       exact;            // 1: every group's rows share one column list (the register-blocked kernels need this); 0: masked blocks, panel kernel only
     int       ngroups;          // groups stored as R x 1 column blocks
     long long nblk;             // blocks in total
     int       nrest;            // rows left to the row-split kernel
@@ -65,6 +66,35 @@ struct crp_rowgroup
     double    *d_bval;          // nblk * R: values, the R rows of a block contiguous
     float     *d_bval32;        // fp32 copy, made on the first fp32 exec
     int       *d_rest;          // nrest: row ids for the row-split kernel
+};
+
+// B-row-panel form of the row groups (spmm_panel.cu / panel_build.hpp): tiles of K groups whose B rows are staged
+// once per thread block in shared memory by cp.async.bulk
+struct crp_rowgroup_host;
+struct crp_panel
+{
+    void      *host;            // crp_panel_host (structure kept for the lazily built fp32 records and the wait map)
+    int       K, CR, EMAX, R;
+    int       ntiles, nchunks;
+    long long union_rows;       // B rows staged per pass over the matrix
+    int       *d_tile_chunk_ptr;
+    int       *d_ucol;
+    void      *d_chunks[2];     // chunk descriptors, [0] fp64 records, [1] fp32 records
+    unsigned char *d_meta[2];
+    size_t    meta_bytes[2];
+    unsigned  *d_chunk_need;    // multi-GPU: wait slots each chunk depends on (NULL: none)
+    int       nslot;
+};
+
+// what a kernel needs to wait for the neighbours' arrival flags itself (peer-memory transport)
+struct crp_spmm_wait
+{
+    const unsigned *flags;      // this rank's arrival flags, one word per rank
+    const int *wait_idx;        // device: wait slot -> flag index
+    int       nwait;
+    unsigned  epoch;
+    long long timeout_ns;
+    int       *err;             // pinned host word set on timeout
 };
 
 struct crp_spmm_plan
@@ -84,11 +114,17 @@ struct crp_spmm_plan
     // nnz-balanced handling of very long rows (power-law matrices), see spmm_longrow.cu
     crp_longrows lr;
     crp_rowgroup rg;
+    crp_rowgroup_host *rg_host; // host copy of the row-group arrays (panel construction)
+    crp_panel pn;
     char      kernel_name[64];
 };
 
 void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val, std::vector<int> *rest_out);
 void crp_rowgroup_destroy(crp_spmm_plan *plan);
+void crp_panel_build(crp_spmm_plan *plan);
+void crp_panel_destroy(crp_spmm_plan *plan);
+// recv_off[j] .. recv_off[j + 1]: rows of the receive buffer that come from the rank of wait slot j (nslot <= 32)
+void crp_panel_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *recv_off);
 // rows: the row ids the row-split kernel is responsible for (NULL = all m rows)
 void crp_longrows_build(crp_spmm_plan *plan, const int *rowptr, const int *rows, const int nrows);
 void crp_longrows_destroy(crp_spmm_plan *plan);

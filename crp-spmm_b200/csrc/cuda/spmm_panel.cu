@@ -1,0 +1,550 @@
+// spmm_panel.cu - row-group CSR x dense kernel with the B rows of a tile staged ONCE per thread block
+// in shared memory by the TMA engine (cp.async.bulk + mbarrier pipeline), warp-specialised.
+//
+// Replaces the mkl_sparse_d_mm call at reference src/rowpara_spmm.c:404-407 for matrices with
+// row-group structure (FEM / multi-dof), like spmm_rowgroup.cu, and removes what limited that kernel
+// (round-1 ncu: 3.0x the algorithmic bytes moved L2 -> L1 because every warp fetched "its" B rows
+// itself, 12 warps / SM waiting on those gathers, fp64 pipe 45 % busy):
+//
+//   * a TILE of K consecutive row groups is owned by one persistent thread block; the union of the
+//     groups' column lists - the tile's B row panel - is copied global -> shared exactly once, one
+//     cp.async.bulk per B row slice (UBLKCP), by a PRODUCER warp that runs NSTAGE - 1 chunks ahead of
+//     the math (mbarrier full / empty ring, expect_tx byte counts: SYNCS.ARRIVE.TRANS64);
+//   * the chunk's block values / row slots arrive in the same stage as one contiguous record
+//     (panel_build.hpp), so the K CONSUMER warps touch global memory only to store C: their inner
+//     loop is LDS (29 cycles) + R * U * VEC FMAs per block, no long-scoreboard dependency at all;
+//   * tiles are dealt round-robin to the blocks, so at any time the whole grid works on a contiguous
+//     window of rows and the panel rows shared between neighbouring tiles are L2 hits;
+//   * (multi-GPU) the producer is the only warp that touches B: it can wait for a neighbour's arrival
+//     flag right before the first chunk that needs a received row, so the product of the own rows
+//     overlaps the exchange inside one kernel (see crp_cuda_spmm_exec_wait).
+//
+// Bound: HBM for A (values travel inside the meta records), first touch of B and C; shared-memory
+// bandwidth (fill + R-fold reuse reads) and fp64 issue inside the SM.  DESIGN.md has the numbers.
+#include <cstring>
+#include <vector>
+
+#include "crp_cuda_internal.cuh"
+#include "panel_build.hpp"
+
+// ---------------------------------------------------------------------------------- PTX helpers
+namespace {
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, const unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, const unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, const unsigned parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`; size and both addresses multiples of 16
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, const unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T, int VEC> struct pvec;
+template <> struct pvec<double, 2>
+{
+    static __device__ __forceinline__ void lds(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void ldc(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void st(double *p, const double (&v)[2]) { __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1])); }
+};
+template <> struct pvec<float, 4>
+{
+    static __device__ __forceinline__ void lds(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void ldc(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void st(float *p, const float (&v)[4]) { __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3])); }
+};
+
+// the R values of one entry from shared memory (broadcast reads), widest access the entry stride allows
+template <typename T, int R>
+__device__ __forceinline__ void lds_vals(const T *p, T (&a)[R])
+{
+    constexpr int BYTES = R * (int) sizeof(T);
+    if constexpr (BYTES % 16 == 0)
+    {
+        #pragma unroll
+        for (int i = 0; i < BYTES / 16; i++)
+        {
+            const uint4 t = reinterpret_cast<const uint4 *>(p)[i];
+            memcpy(reinterpret_cast<char *>(a) + 16 * i, &t, 16);
+        }
+    } else if constexpr (BYTES % 8 == 0) {
+        #pragma unroll
+        for (int i = 0; i < BYTES / 8; i++)
+        {
+            const uint2 t = reinterpret_cast<const uint2 *>(p)[i];
+            memcpy(reinterpret_cast<char *>(a) + 8 * i, &t, 8);
+        }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < R; i++) a[i] = p[i];
+    }
+}
+
+}   // namespace
+
+enum { CRP_PANEL_MAXSTAGE = 8, CRP_PANEL_BAR_BYTES = 128 };
+
+template <typename T>
+struct panel_args
+{
+    const int *tile_chunk_ptr;          // ntiles + 1
+    const crp_panel_chunk *chunks;      // nchunks + 1 (stop record last)
+    const int *ucol;
+    const unsigned char *meta;
+    int ntiles, nchunks;
+    int CR, nstage;
+    unsigned meta_max;                  // bytes reserved per stage for a meta record
+    const char *X0;  size_t ldx0;       // bytes
+    const char *X1;  size_t ldx1;
+    int x0_rows;
+    int n;                              // dense columns
+    T alpha, beta;
+    T *C;  size_t ldc;                  // elements
+    // multi-GPU: chunks that read received rows wait for the arrival flags of the ranks that sent them
+    const unsigned *chunk_need;         // per chunk: bit j = needs wait slot j (NULL: nothing to wait for)
+    const unsigned *flags;              // arrival flags (one 32-bit word per rank)
+    const int *wait_idx;                // wait slot -> flag index
+    int nwait;
+    unsigned epoch;
+    long long timeout_ns;
+    int *err;
+};
+
+template <typename T, int VEC, int R, int U, int K>
+__global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kernel(const panel_args<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int W = 32 * U * VEC;                         // dense columns per block
+    constexpr int RBW = W * (int) sizeof(T);                // bytes per staged row slice
+    constexpr int HDR = ((3 + 2 * K + 3) / 4) * 16;
+    constexpr unsigned FULLMASK = (1u << R) - 1u;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + CRP_PANEL_MAXSTAGE;
+    unsigned char *rows = smem + CRP_PANEL_BAR_BYTES;
+    unsigned char *metas = rows + (size_t) a.nstage * a.CR * RBW;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nstage = a.nstage;
+    const int col0 = blockIdx.y * W;
+    const int ncols = min(a.n - col0, W);
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < nstage; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0)
+    {
+        // ------------------------------------------------------------------ producer
+        const unsigned rb = (unsigned) ncols * (unsigned) sizeof(T);
+        const char *x0 = a.X0 + (size_t) col0 * sizeof(T);
+        const char *x1 = a.X1 + (size_t) col0 * sizeof(T);
+        unsigned seen = 0;                                  // wait slots whose flag has been observed
+        int s = 0;
+        unsigned ph = 1;                                    // parity the empty barrier of stage s is waited on
+        int t = blockIdx.x;
+        int c = -1, cend = -1;
+        if (t < a.ntiles) { c = __ldg(a.tile_chunk_ptr + t); cend = __ldg(a.tile_chunk_ptr + t + 1); }
+        for (;;)
+        {
+            const int cc = (c >= 0) ? c : a.nchunks;        // the stop record closes the stream
+            const int4 dv = __ldg(reinterpret_cast<const int4 *>(a.chunks) + cc);
+            const int uo0 = dv.x, nrows = dv.y;
+            const unsigned mo16 = (unsigned) dv.z, mbytes = (unsigned) dv.w * 16u;
+            int mycol = (lane < nrows) ? __ldg(a.ucol + uo0 + lane) : 0;
+            if (a.chunk_need != NULL && c >= 0)
+            {
+                unsigned need = __ldg(a.chunk_need + cc) & ~seen;
+                if (need)
+                {
+                    // one lane per missing neighbour spins on its arrival flag; rows written by the peer's stores
+                    // are ordered before the flag (st.release.sys after __threadfence_system on the sender)
+                    if (lane < a.nwait && ((need >> lane) & 1u))
+                    {
+                        const unsigned *f = a.flags + a.wait_idx[lane];
+                        long long t0;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                        while ((int) (ld_acquire_sys(f) - a.epoch) < 0)
+                        {
+                            long long t1;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                            if (t1 - t0 > a.timeout_ns) { *a.err = 1; break; }
+                            __nanosleep(100);
+                        }
+                    }
+                    __syncwarp();
+                    asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy acquire -> async-proxy (TMA) reads
+                    seen |= need;
+                }
+            }
+            mbar_wait(&empty[s], ph);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (unsigned) nrows * rb + mbytes);
+            __syncwarp();
+            if (lane == 0) bulk_g2s(metas + (size_t) s * a.meta_max, a.meta + (size_t) mo16 * 16, mbytes, &full[s]);
+            unsigned char *dst = rows + (size_t) s * a.CR * RBW;
+            for (int r = lane; r < nrows; r += 32)
+            {
+                if (r >= 32) mycol = __ldg(a.ucol + uo0 + r);
+                const char *src = (mycol < a.x0_rows) ? x0 + (size_t) mycol * a.ldx0 : x1 + (size_t) (mycol - a.x0_rows) * a.ldx1;
+                bulk_g2s(dst + (size_t) r * RBW, src, rb, &full[s]);
+            }
+            if (++s == nstage) { s = 0; ph ^= 1u; }
+            if (c < 0) break;
+            if (++c >= cend)
+            {
+                t += gridDim.x;
+                if (t < a.ntiles) { c = __ldg(a.tile_chunk_ptr + t); cend = __ldg(a.tile_chunk_ptr + t + 1); }
+                else c = -1;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int w = warp - 1;
+    int voff[U];                                            // element offset of this lane's column vectors; -1: beyond the slice
+    #pragma unroll
+    for (int u = 0; u < U; u++) { const int v = (u * 32 + lane) * VEC; voff[u] = (v < ncols) ? v : -1; }
+
+    T acc[R][U][VEC];
+    int row0 = -1;
+    int s = 0;
+    unsigned ph = 0;                                        // parity the full barrier of stage s is waited on
+    for (;; s = (s + 1 == nstage) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u)
+    {
+        mbar_wait(&full[s], ph);
+        const unsigned char *mrec = metas + (size_t) s * a.meta_max;
+        const int *hdr = reinterpret_cast<const int *>(mrec);
+        const int flags = hdr[1];
+        if (flags & CRP_PANEL_STOP) break;
+        const int e0 = hdr[2 + K + w], e1 = hdr[3 + K + w], ne = hdr[2 + 2 * K];
+        if (flags & CRP_PANEL_FIRST)
+        {
+            row0 = hdr[2 + w];
+            #pragma unroll
+            for (int r = 0; r < R; r++)
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                    #pragma unroll
+                    for (int e = 0; e < VEC; e++) acc[r][u][e] = (T) 0;
+        }
+        const unsigned *slots = reinterpret_cast<const unsigned *>(mrec + HDR);
+        const T *vals = reinterpret_cast<const T *>(mrec + HDR + (((size_t) ne * 4 + 15) & ~(size_t) 15));
+        const T *xs = reinterpret_cast<const T *>(rows + (size_t) s * a.CR * RBW);
+
+        auto load = [&](const int e, unsigned &sm, T (&av)[R], T (&xv)[U][VEC]) {
+            sm = slots[e];
+            lds_vals<T, R>(vals + (size_t) e * R, av);
+            const T *xr = xs + (size_t) (sm & 0xffffu) * W;
+            #pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (voff[u] >= 0) pvec<T, VEC>::lds(xr + voff[u], xv[u]);
+                else { for (int q = 0; q < VEC; q++) xv[u][q] = (T) 0; }
+            }
+        };
+        auto fmas = [&](const unsigned sm, const T (&av)[R], const T (&xv)[U][VEC]) {
+            if ((sm >> 16) == FULLMASK)
+            {
+                #pragma unroll
+                for (int r = 0; r < R; r++)
+                    #pragma unroll
+                    for (int u = 0; u < U; u++)
+                        #pragma unroll
+                        for (int q = 0; q < VEC; q++) acc[r][u][q] = fma(av[r], xv[u][q], acc[r][u][q]);
+            } else {
+                // near-identical group: rows that do not have this column are skipped, never multiplied by a stored zero
+                #pragma unroll
+                for (int r = 0; r < R; r++)
+                    if ((sm >> (16 + r)) & 1u)
+                    {
+                        #pragma unroll
+                        for (int u = 0; u < U; u++)
+                            #pragma unroll
+                            for (int q = 0; q < VEC; q++) acc[r][u][q] = fma(av[r], xv[u][q], acc[r][u][q]);
+                    }
+            }
+        };
+
+        int e = e0;
+        if (e < e1)
+        {
+            unsigned sa, sb;
+            T aa[R], ab[R], xa[U][VEC], xb[U][VEC];
+            load(e, sa, aa, xa);
+            for (;;)
+            {
+                if (e + 1 < e1) load(e + 1, sb, ab, xb);
+                fmas(sa, aa, xa);
+                if (++e >= e1) break;
+                if (e + 1 < e1) load(e + 1, sa, aa, xa);
+                fmas(sb, ab, xb);
+                if (++e >= e1) break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);              // this warp is done with stage s
+
+        if ((flags & CRP_PANEL_LAST) && row0 >= 0)
+        {
+            #pragma unroll
+            for (int r = 0; r < R; r++)
+            {
+                T *crow = a.C + (size_t) (row0 + r) * a.ldc + col0;
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                {
+                    if (voff[u] < 0) continue;
+                    T out[VEC];
+                    if (a.beta == (T) 0)
+                    {
+                        #pragma unroll
+                        for (int q = 0; q < VEC; q++) out[q] = a.alpha * acc[r][u][q];
+                    } else {
+                        T old[VEC];
+                        pvec<T, VEC>::ldc(crow + voff[u], old);
+                        #pragma unroll
+                        for (int q = 0; q < VEC; q++) out[q] = fma(a.alpha, acc[r][u][q], a.beta * old[q]);
+                    }
+                    pvec<T, VEC>::st(crow + voff[u], out);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ plan side (host)
+
+static int panel_env_int(const char *name, const int dflt)
+{
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+static void *panel_upload(const void *src, const size_t bytes)
+{
+    void *d = NULL;
+    if (bytes == 0) return d;
+    CRP_CUDA_CHECK(cudaMalloc(&d, bytes));
+    CRP_CUDA_CHECK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    return d;
+}
+
+// Build the panel form for the plan's row groups (called once at plan creation; the meta records of a value type
+// are made on the first exec with that type).  Parameters: CRP_PANEL_K (8 or 12 groups per tile), CRP_PANEL_CR rows and
+// CRP_PANEL_EMAX blocks per chunk; defaults sized so that three to four stages of 2 KB row slices fit into 227 KB.
+void crp_panel_build(crp_spmm_plan *plan)
+{
+    crp_panel *pn = &plan->pn;
+    memset(pn, 0, sizeof(*pn));
+    const crp_rowgroup_host *rg = plan->rg_host;
+    if (rg == NULL || rg->R < 2 || rg->g_row.empty() || plan->n_hint < 64) return;
+    if (panel_env_int("CRP_SPMM_PANEL", 1) == 0) return;
+    int K = panel_env_int("CRP_PANEL_K", 8);
+    if (K != 8 && K != 12) K = 8;
+    int CR = panel_env_int("CRP_PANEL_CR", 32);
+    if (CR < 4) CR = 4;
+    if (CR > 64) CR = 64;
+    int EMAX = panel_env_int("CRP_PANEL_EMAX", 4 * CR);
+    if (EMAX < K) EMAX = K;
+    crp_panel_host *ph = new crp_panel_host();
+    crp_panel_build_structure(*rg, K, CR, EMAX, ph);
+    pn->host = ph;
+    pn->K = K;  pn->CR = CR;  pn->EMAX = EMAX;  pn->R = rg->R;
+    pn->ntiles = ph->ntiles;  pn->nchunks = ph->nchunks();  pn->union_rows = (long long) ph->ucol.size();
+    pn->d_tile_chunk_ptr = (int *) panel_upload(ph->tile_chunk_ptr.data(), sizeof(int) * ph->tile_chunk_ptr.size());
+    pn->d_ucol = (int *) panel_upload(ph->ucol.data(), sizeof(int) * ph->ucol.size());
+}
+
+template <typename T>
+static void panel_make_meta(crp_spmm_plan *plan)
+{
+    crp_panel *pn = &plan->pn;
+    const int slot = (sizeof(T) == 8) ? 0 : 1;
+    if (pn->d_meta[slot] != NULL) return;
+    crp_panel_host *ph = (crp_panel_host *) pn->host;
+    std::vector<unsigned char> meta;
+    crp_panel_fill_meta<T>(*plan->rg_host, ph, &meta);
+    pn->d_meta[slot] = (unsigned char *) panel_upload(meta.data(), meta.size());
+    pn->d_chunks[slot] = panel_upload(ph->chunks.data(), sizeof(crp_panel_chunk) * ph->chunks.size());
+    pn->meta_bytes[slot] = meta.size();
+}
+
+void crp_panel_destroy(crp_spmm_plan *plan)
+{
+    crp_panel *pn = &plan->pn;
+    if (pn->d_tile_chunk_ptr) CRP_CUDA_CHECK(cudaFree(pn->d_tile_chunk_ptr));
+    if (pn->d_ucol) CRP_CUDA_CHECK(cudaFree(pn->d_ucol));
+    if (pn->d_chunk_need) CRP_CUDA_CHECK(cudaFree(pn->d_chunk_need));
+    for (int i = 0; i < 2; i++)
+    {
+        if (pn->d_meta[i]) CRP_CUDA_CHECK(cudaFree(pn->d_meta[i]));
+        if (pn->d_chunks[i]) CRP_CUDA_CHECK(cudaFree(pn->d_chunks[i]));
+    }
+    delete (crp_panel_host *) pn->host;
+    memset(pn, 0, sizeof(*pn));
+}
+
+// Per chunk, which neighbours' rows it reads: bit j set = a row received from the rank of wait slot j
+// (recv_off[j] .. recv_off[j + 1] are that rank's rows in the receive buffer, i.e. virtual ids x0_rows + ...).
+void crp_panel_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *recv_off)
+{
+    crp_panel *pn = &plan->pn;
+    if (pn->d_chunk_need) { CRP_CUDA_CHECK(cudaFree(pn->d_chunk_need)); pn->d_chunk_need = NULL; }
+    pn->nslot = 0;
+    if (pn->host == NULL || nslot <= 0 || nslot > 32) return;      // more than 32 neighbours: the caller keeps the separate wait kernel
+    const crp_panel_host *ph = (const crp_panel_host *) pn->host;
+    std::vector<unsigned> need((size_t) ph->nchunks() + 1, 0u);
+    bool any = false;
+    for (int c = 0; c < ph->nchunks(); c++)
+    {
+        unsigned m = 0;
+        for (int r = 0; r < ph->chunks[c].nrows; r++)
+        {
+            const int v = ph->ucol[(size_t) ph->chunks[c].uo0 + r] - plan->x0_rows;
+            if (v < 0) continue;
+            int j = 0;
+            while (j + 1 < nslot && v >= recv_off[j + 1]) j++;
+            m |= 1u << j;
+        }
+        need[c] = m;
+        any = any || m != 0;
+    }
+    if (any) pn->d_chunk_need = (unsigned *) panel_upload(need.data(), sizeof(unsigned) * need.size());
+    pn->nslot = nslot;
+}
+
+// ------------------------------------------------------------------------------------- launch
+
+template <typename T, int VEC, int R, int U, int K>
+static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cudaStream_t s)
+{
+    crp_panel *pn = &plan->pn;
+    panel_args<T> args = args0;
+    constexpr int W = 32 * U * VEC, RBW = W * (int) sizeof(T);
+    const crp_panel_host *ph = (const crp_panel_host *) pn->host;
+    args.meta_max = (unsigned) ph->meta_max(sizeof(T));
+    const size_t stage = (size_t) pn->CR * RBW + args.meta_max;
+    int dev = 0, smem_max = 0, nsm = 0;
+    CRP_CUDA_CHECK(cudaGetDevice(&dev));
+    CRP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CRP_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    int nstage = (int) (((size_t) smem_max - CRP_PANEL_BAR_BYTES) / stage);
+    if (nstage > CRP_PANEL_MAXSTAGE) nstage = CRP_PANEL_MAXSTAGE;
+    const int want = panel_env_int("CRP_PANEL_STAGES", 0);
+    if (want >= 2 && want < nstage) nstage = want;
+    if (nstage < 2) return false;
+    args.nstage = nstage;
+    const size_t smem = CRP_PANEL_BAR_BYTES + (size_t) nstage * stage;
+    auto kern = spmm_panel_kernel<T, VEC, R, U, K>;
+    static bool attr_set = false;
+    if (!attr_set) { CRP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); attr_set = true; }
+    const int nslice = (args.n + W - 1) / W;
+    int gx = nsm / nslice;
+    const int gx_env = panel_env_int("CRP_PANEL_GRID", 0);
+    if (gx_env > 0) gx = gx_env;
+    if (gx < 1) gx = 1;
+    if (gx > pn->ntiles) gx = pn->ntiles;
+    kern<<<dim3((unsigned) gx, (unsigned) nslice), (K + 1) * 32, smem, s>>>(args);
+    CRP_LAUNCH_CHECK();
+    return true;
+}
+
+template <typename T, int VEC, int R>
+static bool panel_launch_R(crp_spmm_plan *plan, const panel_args<T> &args, cudaStream_t s)
+{
+    const int nv = args.n / VEC;
+    const int K = plan->pn.K;
+    constexpr int UMAX = (R * VEC * (int) sizeof(T) <= 6 * 16) ? 4 : 2;      // accumulator tile <= 96 registers, as in spmm_rowgroup.cu
+#define CRP_PN(U, K_) panel_launch_cfg<T, VEC, R, (U <= UMAX ? U : UMAX), K_>(plan, args, s)
+    if (K == 12)
+    {
+        if (nv >= 128) return CRP_PN(4, 12);
+        if (nv >= 64)  return CRP_PN(2, 12);
+        return CRP_PN(1, 12);
+    }
+    if (nv >= 128) return CRP_PN(4, 8);
+    if (nv >= 64)  return CRP_PN(2, 8);
+    return CRP_PN(1, 8);
+#undef CRP_PN
+}
+
+// false: the panel form does not apply to this call (no panel, misaligned operands, narrow n) - the caller falls back
+// to the row-group kernel.  wait != NULL: the kernel itself waits for the neighbours' arrival flags (peer-memory transport).
+template <typename T, int VEC>
+bool crp_launch_panel(
+    crp_spmm_plan *plan, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc,
+    const crp_spmm_wait *wait, cudaStream_t s
+)
+{
+    crp_panel *pn = &plan->pn;
+    if (pn->host == NULL || pn->ntiles == 0) return false;
+    const size_t es = sizeof(T);
+    if (n < 64 || (n * es) % 16 != 0 || (ldx0 * es) % 16 != 0 || (X1 != NULL && (ldx1 * es) % 16 != 0) || (ldc * es) % 16 != 0) return false;
+    if ((((uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C) & 15) != 0) return false;
+    panel_make_meta<T>(plan);
+    const int slot = (es == 8) ? 0 : 1;
+    panel_args<T> a;
+    memset(&a, 0, sizeof(a));
+    a.tile_chunk_ptr = pn->d_tile_chunk_ptr;
+    a.chunks = (const crp_panel_chunk *) pn->d_chunks[slot];
+    a.ucol = pn->d_ucol;
+    a.meta = pn->d_meta[slot];
+    a.ntiles = pn->ntiles;  a.nchunks = pn->nchunks;
+    a.CR = pn->CR;
+    a.X0 = (const char *) X0;  a.ldx0 = ldx0 * es;
+    a.X1 = (const char *) X1;  a.ldx1 = ldx1 * es;
+    a.x0_rows = plan->x0_rows;
+    a.n = n;
+    a.alpha = alpha;  a.beta = beta;
+    a.C = C;  a.ldc = ldc;
+    if (wait != NULL && wait->nwait > 0 && pn->d_chunk_need != NULL)
+    {
+        a.chunk_need = pn->d_chunk_need;
+        a.flags = wait->flags;  a.wait_idx = wait->wait_idx;  a.nwait = wait->nwait;
+        a.epoch = wait->epoch;  a.timeout_ns = wait->timeout_ns;  a.err = wait->err;
+    }
+    switch (pn->R)
+    {
+        case 2: return panel_launch_R<T, VEC, 2>(plan, a, s);
+        case 3: return panel_launch_R<T, VEC, 3>(plan, a, s);
+        case 4: return panel_launch_R<T, VEC, 4>(plan, a, s);
+        case 6: return panel_launch_R<T, VEC, 6>(plan, a, s);
+        case 8: return panel_launch_R<T, VEC, 8>(plan, a, s);
+        default: return false;
+    }
+}
+
+template bool crp_launch_panel<double, 2>(crp_spmm_plan *, const int, const double *, size_t, const double *, size_t, double, double, double *, size_t, const crp_spmm_wait *, cudaStream_t);
+template bool crp_launch_panel<float, 4>(crp_spmm_plan *, const int, const float *, size_t, const float *, size_t, float, float, float *, size_t, const crp_spmm_wait *, cudaStream_t);

@@ -15,6 +15,11 @@ void crp_launch_rowsplit(
 template <typename T>
 void crp_launch_longrow_reduce(const crp_longrows *lr, const int n, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
 template <typename T, int VEC>
+bool crp_launch_panel(
+    crp_spmm_plan *plan, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc,
+    const crp_spmm_wait *wait, cudaStream_t s
+);
+template <typename T, int VEC>
 void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
 
 extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int x0_rows, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint)
@@ -105,17 +110,39 @@ static void rowsplit_balanced(
     crp_launch_longrow_reduce<T>(lr, n, alpha, beta, C, ldc, s);
 }
 
+// A kernel that cannot wait for the neighbours' flags itself is preceded by the plain wait kernel.
+static void wait_first(const crp_spmm_wait *wait, cudaStream_t s)
+{
+    if (wait == NULL || wait->nwait <= 0) return;
+    crp_cuda_wait_flags(wait->flags, wait->wait_idx, wait->nwait, wait->epoch, 1e-9 * (double) wait->timeout_ns, wait->err, (void *) s);
+}
+
 template <typename T, int VECN>
 static void spmm_dispatch(
     crp_spmm_plan *plan, const T *val, const T *bval, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1,
-    T alpha, T beta, T *C, size_t ldc, cudaStream_t s, const char *tname
+    T alpha, T beta, T *C, size_t ldc, const crp_spmm_wait *wait, cudaStream_t s, const char *tname
 )
 {
     const int x0_rows = plan->x0_rows;
     const crp_rowgroup *rg = &plan->rg;
     const bool want_rg = (plan->variant == CRP_VARIANT_AUTO || plan->variant == CRP_VARIANT_ROWGROUP);
     const char *lr_tag = (plan->lr.nlong > 0) ? "+longrow" : "";
-    if (want_rg && rg->R > 1 && rg->ngroups > 0)
+    const bool want_pn = (plan->variant == CRP_VARIANT_AUTO || plan->variant == CRP_VARIANT_PANEL);
+    if (want_pn && rg->R > 1 && rg->ngroups > 0)
+    {
+        // the rest rows go first when the panel kernel does the waiting: they may need received rows too
+        if (rg->nrest > 0) wait_first(wait, s);
+        if (crp_launch_panel<T, VECN>(plan, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, rg->nrest > 0 ? NULL : wait, s))
+        {
+            if (rg->nrest > 0) rowsplit_balanced<T, VECN>(plan, true, rg->nrest, rg->d_rest, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s);
+            snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_panel_%s_R%d_K%d%s%s", tname, rg->R, plan->pn.K, rg->nrest > 0 ? "+rowsplit" : "", rg->nrest > 0 ? lr_tag : "");
+            plan->last_kernel = plan->kernel_name;
+            return;
+        }
+        if (rg->nrest > 0) wait = NULL;          // already waited
+    }
+    wait_first(wait, s);
+    if (want_rg && rg->R > 1 && rg->ngroups > 0 && rg->exact)
     {
         const uintptr_t ptrs = (uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C;
         const bool vec_ok = (n % VECN == 0) && (ldx0 % VECN == 0) && (X1 == NULL || ldx1 % VECN == 0) && (ldc % VECN == 0) && ((ptrs & 15) == 0);
@@ -125,7 +152,7 @@ static void spmm_dispatch(
         snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowgroup_%s_R%d%s%s", tname, rg->R, rg->nrest > 0 ? "+rowsplit" : "", rg->nrest > 0 ? lr_tag : "");
     } else {
         // forcing "rowsplit" on a plan that has a row-group form: the segment lists were built for the rest rows only
-        const bool use_lr = (rg->R <= 1) && plan->variant != CRP_VARIANT_ROWSPLIT;
+        const bool use_lr = (rg->R <= 1) && plan->variant != CRP_VARIANT_ROWSPLIT && plan->variant != CRP_VARIANT_MERGEPATH;
         rowsplit_balanced<T, VECN>(plan, use_lr, plan->m, NULL, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s);
         snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_rowsplit_%s%s", tname, use_lr ? lr_tag : "");
     }
@@ -138,22 +165,56 @@ extern "C" void crp_cuda_spmm_exec(
     const double beta, void *C, const int ldc, void *stream
 )
 {
+    crp_cuda_spmm_exec_wait(plan, n, elem_size, alpha, X0, ldx0, X1, ldx1, beta, C, ldc, NULL, NULL, 0, 0, 0.0, NULL, stream);
+}
+
+extern "C" void crp_cuda_spmm_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *recv_off)
+{
+    if (plan != NULL) crp_panel_set_wait_map(plan, nslot, recv_off);
+}
+
+extern "C" void crp_cuda_spmm_exec_wait(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
+    const void *X0, const int ldx0, const void *X1, const int ldx1,
+    const double beta, void *C, const int ldc,
+    const unsigned int *flags_d, const int *wait_idx_d, const int nwait, const unsigned int epoch, const double timeout_s, int *err,
+    void *stream
+)
+{
     if (plan == NULL) { fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: NULL plan\n"); abort(); }
-    if (plan->m == 0 || n <= 0) return;
     cudaStream_t s = as_stream(stream);
+    crp_spmm_wait wt, *wait = NULL;
+    if (nwait > 0)
+    {
+        wt.flags = flags_d;  wt.wait_idx = wait_idx_d;  wt.nwait = nwait;  wt.epoch = epoch;
+        wt.timeout_ns = (long long) (timeout_s * 1e9);  wt.err = err;
+        wait = &wt;
+    }
+    if (plan->m == 0 || n <= 0) { wait_first(wait, s); return; }
     if (elem_size == 8)
     {
         spmm_dispatch<double, 2>(plan, plan->d_val, plan->rg.d_bval, n, (const double *) X0, (size_t) ldx0, (const double *) X1, (size_t) ldx1,
-                                 alpha, beta, (double *) C, (size_t) ldc, s, "f64");
+                                 alpha, beta, (double *) C, (size_t) ldc, wait, s, "f64");
     } else if (elem_size == 4) {
         cast_to_f32(plan->d_val, &plan->d_val32, (size_t) plan->nnz, s);
         cast_to_f32(plan->rg.d_bval, &plan->rg.d_bval32, (size_t) plan->rg.nblk * (size_t) plan->rg.R, s);
         spmm_dispatch<float, 4>(plan, plan->d_val32, plan->rg.d_bval32, n, (const float *) X0, (size_t) ldx0, (const float *) X1, (size_t) ldx1,
-                                (float) alpha, (float) beta, (float *) C, (size_t) ldc, s, "f32");
+                                (float) alpha, (float) beta, (float *) C, (size_t) ldc, wait, s, "f32");
     } else {
         fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: elem_size must be 4 or 8\n");
         abort();
     }
+}
+
+extern "C" void crp_cuda_spmm_plan_info(const crp_spmm_plan *plan, long long out[12])
+{
+    for (int i = 0; i < 12; i++) out[i] = 0;
+    if (plan == NULL) return;
+    out[0] = plan->rg.R > 1 ? plan->rg.R : 1;
+    out[1] = plan->rg.ngroups;  out[2] = plan->rg.nblk;  out[3] = plan->rg.R > 1 ? plan->rg.nrest : plan->m;
+    out[4] = plan->rg.R > 1 ? plan->rg.rest_nnz : plan->nnz;
+    out[5] = plan->pn.ntiles;  out[6] = plan->pn.nchunks;  out[7] = plan->pn.union_rows;
+    out[8] = plan->rg.exact;  out[9] = plan->lr.nlong;  out[10] = plan->nnz;  out[11] = 0;
 }
 
 extern "C" const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan) { return plan ? plan->last_kernel : "none"; }
@@ -164,6 +225,7 @@ extern "C" void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name)
     if (strcmp(name, "rowsplit") == 0) plan->variant = CRP_VARIANT_ROWSPLIT;
     else if (strcmp(name, "rowgroup") == 0) plan->variant = CRP_VARIANT_ROWGROUP;
     else if (strcmp(name, "mergepath") == 0) plan->variant = CRP_VARIANT_MERGEPATH;
+    else if (strcmp(name, "panel") == 0) plan->variant = CRP_VARIANT_PANEL;
     else plan->variant = CRP_VARIANT_AUTO;
 }
 

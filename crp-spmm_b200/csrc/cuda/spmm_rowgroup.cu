@@ -24,73 +24,40 @@
 #include <vector>
 
 #include "crp_cuda_internal.cuh"
+#include "rowgroup_build.hpp"
 
 // ------------------------------------------------------------------ plan-time analysis (host)
+// The analysis itself is rowgroup_build.hpp (pure C++, also exercised by the CPU tests).
 
-static const int kCandR[] = { 8, 6, 4, 3, 2 };
-
-// Row i "continues" row i - 1 when both have exactly the same column list; a group of R rows starting
-// at r0 is usable ("perfect") when rows r0 + 1 .. r0 + R - 1 all continue their predecessor, the list is
-// non-empty and strictly increasing.  Groups start at row `off` + multiples of R: the first local row of a
-// rank is generally not aligned with the matrix's own block structure, so every offset is tried.
-// Cost unit: L1 wavefronts per 64 B of C row (4 per B-row load + 1 per row FMA'd), see DESIGN.md.
-struct rg_rowinfo
+static double rg_min_fill()
 {
-    std::vector<unsigned char> cont;    // row i has the same columns as row i - 1
-    std::vector<unsigned char> incr;    // row i's columns are strictly increasing and the row is not empty
-};
-
-static void rg_scan_rows(const int m, const int *rowptr, const int *colidx, rg_rowinfo *ri)
-{
-    ri->cont.assign((size_t) m, 0);
-    ri->incr.assign((size_t) m, 0);
-    for (int i = 0; i < m; i++)
-    {
-        const int b = rowptr[i], len = rowptr[i + 1] - b;
-        bool inc = len > 0;
-        for (int p = b + 1; inc && p < b + len; p++) if (colidx[p] <= colidx[p - 1]) inc = false;
-        ri->incr[(size_t) i] = inc;
-        if (i > 0 && len > 0 && rowptr[i] - rowptr[i - 1] == len)
-            ri->cont[(size_t) i] = (memcmp(colidx + b, colidx + rowptr[i - 1], sizeof(int) * (size_t) len) == 0);
-    }
+    // relaxed (masked) groups: CRP_SPMM_RG_FILL = minimum fraction of real nonzeros in a group's R x |union| slots;
+    // 1.0 = exact groups only
+    const char *e = getenv("CRP_SPMM_RG_FILL");
+    double f = (e && e[0]) ? atof(e) : 0.75;
+    if (f < 0.05) f = 0.05;
+    if (f > 1.0) f = 1.0;
+    return f;
 }
 
-static inline bool rg_group_ok(const rg_rowinfo &ri, const int r0, const int R, const int m)
+static crp_rg_choice rg_decide(const int m, const int *rowptr, const int *colidx, const crp_rg_rowinfo &ri, const int forced, const int n_hint)
 {
-    if (r0 + R > m || !ri.incr[(size_t) r0]) return false;
-    for (int r = r0 + 1; r < r0 + R; r++) if (!ri.cont[(size_t) r]) return false;
-    return true;
-}
-
-static double analyse_R(const int m, const int *rowptr, const rg_rowinfo &ri, const int R, const int off, long long *nblk_out, long long *rest_nnz_out)
-{
-    long long nblk = 0;
-    for (int r0 = off; r0 + R <= m; r0 += R)
-        if (rg_group_ok(ri, r0, R, m)) nblk += rowptr[r0 + 1] - rowptr[r0];
-    const long long rest = (long long) rowptr[m] - nblk * R;
-    *nblk_out = nblk;
-    *rest_nnz_out = rest;
-    return (double) nblk * (4.0 + R) + (double) rest * 5.0;
-}
-
-// the group size and alignment with the lowest modelled cost (R = 1: keep the row-split kernel); forced: CRP_SPMM_ROWGROUP_R
-static void rg_choose(const int m, const int *rowptr, const rg_rowinfo &ri, const int forced, int *best_R_, int *best_off_, long long *nblk_)
-{
-    double best_cost = (double) rowptr[m] * 5.0;      // everything in the row-split kernel
-    int best_R = 1, best_off = 0;
-    long long best_nblk = 0;
-    for (int R : kCandR)
-    {
-        if (forced > 1 && R != forced) continue;
-        for (int off = 0; off < R && off < m; off++)
-        {
-            long long nblk, rest;
-            const double cost = analyse_R(m, rowptr, ri, R, off, &nblk, &rest);
-            const bool take = (forced > 1) ? (nblk > 0 && (best_R == 1 || cost < best_cost)) : (cost < 0.9 * best_cost || (best_R == R && cost < best_cost));
-            if (take) { best_cost = cost; best_R = R; best_off = off; best_nblk = nblk; }
-        }
-    }
-    *best_R_ = best_R;  *best_off_ = best_off;  *nblk_ = best_nblk;
+    // exact groups first (cheap: flags only); relaxed groups are considered when the exact ones leave more than 10 % of the
+    // nonzeros to the row-split kernel, on a sample of the rows, and only where the panel kernel can run them (n >= 64)
+    crp_rg_choice ex = crp_rg_choose(m, rowptr, colidx, ri, forced, 1.0, 0);
+    const long long nnz = (long long) rowptr[m] - rowptr[0];
+    const double fill = rg_min_fill();
+    if (fill >= 1.0 || n_hint < 64 || (ex.R > 1 && ex.grouped_nnz * 10 >= nnz * 9)) return ex;
+    const int sample = 1 << 16;
+    crp_rg_choice rx = crp_rg_choose(m, rowptr, colidx, ri, forced, fill, sample);
+    if (rx.R <= 1) return ex;
+    const int mm = (sample < m) ? sample : m;
+    const long long nnz_s = (long long) rowptr[mm] - rowptr[0];
+    const double frac_rx = nnz_s > 0 ? (double) rx.grouped_nnz / (double) nnz_s : 0.0;
+    const double frac_ex = nnz > 0 ? (double) ex.grouped_nnz / (double) nnz : 0.0;
+    if (ex.R > 1 && frac_rx < frac_ex + 0.05) return ex;
+    rx.all_exact = false;
+    return rx;
 }
 
 // Host-only view of the plan-time decision (no device needed): which group size / alignment would be used for this CSR
@@ -103,9 +70,10 @@ extern "C" void crp_cuda_spmm_analyse(const int m, const int *rowptr, const int 
     if (const char *e = getenv("CRP_SPMM_ROWGROUP_R")) forced = atoi(e);
     if (forced != 1)
     {
-        rg_rowinfo ri;
-        rg_scan_rows(m, rowptr, colidx, &ri);
-        rg_choose(m, rowptr, ri, forced, R, offset, nblk);
+        crp_rg_rowinfo ri;
+        crp_rg_scan_rows(m, rowptr, colidx, &ri);
+        const crp_rg_choice c = crp_rg_choose(m, rowptr, colidx, ri, forced, 1.0, 0);
+        *R = c.R;  *offset = c.off;  *nblk = c.nblk;
     }
     for (int i = 0; i < m; i++) if (rowptr[i + 1] - rowptr[i] > CRP_LONG_ROW) (*n_long_rows)++;
 }
@@ -120,39 +88,20 @@ void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colid
     int forced = 0;
     if (const char *e = getenv("CRP_SPMM_ROWGROUP_R")) forced = atoi(e);      // 0 auto, 1 disable, else force R
     if (forced == 1) return;
-    rg_rowinfo ri;
-    rg_scan_rows(m, rowptr, colidx, &ri);
-    int best_R = 1, best_off = 0;
-    long long best_nblk = 0;
-    rg_choose(m, rowptr, ri, forced, &best_R, &best_off, &best_nblk);
-    if (best_R == 1) return;
+    crp_rg_rowinfo ri;
+    crp_rg_scan_rows(m, rowptr, colidx, &ri);
+    const crp_rg_choice ch = rg_decide(m, rowptr, colidx, ri, forced, plan->n_hint);
+    if (ch.R == 1) return;
 
-    const int R = best_R;
-    std::vector<int> g_row, g_ptr, b_col, rest_rows;
-    std::vector<double> b_val;
-    g_ptr.push_back(0);
+    crp_rowgroup_host *rh = new crp_rowgroup_host();
+    std::vector<int> rest_rows;
     long long rest = 0;
-    for (int r = 0; r < best_off && r < m; r++) { rest_rows.push_back(r); rest += rowptr[r + 1] - rowptr[r]; }
-    for (int r0 = best_off; r0 < m; r0 += R)
-    {
-        const int r1 = std::min(m, r0 + R);
-        if (!rg_group_ok(ri, r0, R, m))
-        {
-            for (int r = r0; r < r1; r++) { rest_rows.push_back(r); rest += rowptr[r + 1] - rowptr[r]; }
-            continue;
-        }
-        g_row.push_back(r0);
-        const int len = rowptr[r0 + 1] - rowptr[r0];
-        for (int j = 0; j < len; j++)
-        {
-            b_col.push_back(colidx[rowptr[r0] + j]);
-            for (int r = 0; r < R; r++) b_val.push_back(val[rowptr[r0 + r] + j]);
-        }
-        g_ptr.push_back((int) b_col.size());
-    }
-    rg->R = R;
-    rg->ngroups = (int) g_row.size();
-    rg->nblk = (long long) b_col.size();
+    crp_rg_build(m, rowptr, colidx, val, ri, ch.R, ch.off, ch.all_exact ? 1.0 : rg_min_fill(), rh, &rest_rows, &rest);
+    if (rh->g_row.empty()) { delete rh; return; }
+    rg->R = ch.R;
+    rg->exact = rh->b_mask.empty() ? 1 : 0;
+    rg->ngroups = (int) rh->g_row.size();
+    rg->nblk = (long long) rh->b_col.size();
     rg->nrest = (int) rest_rows.size();
     rg->rest_nnz = rest;
     auto upload = [](const void *src, size_t bytes) -> void * {
@@ -162,17 +111,26 @@ void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colid
         CRP_CUDA_CHECK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
         return d;
     };
-    rg->d_grow = (int *) upload(g_row.data(), sizeof(int) * g_row.size());
-    rg->d_gptr = (int *) upload(g_ptr.data(), sizeof(int) * g_ptr.size());
-    rg->d_bcol = (int *) upload(b_col.data(), sizeof(int) * b_col.size());
-    rg->d_bval = (double *) upload(b_val.data(), sizeof(double) * b_val.size());
+    if (rg->exact)
+    {
+        // arrays of the register-blocked fallback kernels below (the panel kernel has its own records)
+        rg->d_grow = (int *) upload(rh->g_row.data(), sizeof(int) * rh->g_row.size());
+        rg->d_gptr = (int *) upload(rh->g_ptr.data(), sizeof(int) * rh->g_ptr.size());
+        rg->d_bcol = (int *) upload(rh->b_col.data(), sizeof(int) * rh->b_col.size());
+        rg->d_bval = (double *) upload(rh->b_val.data(), sizeof(double) * rh->b_val.size());
+    }
     rg->d_rest = (int *) upload(rest_rows.data(), sizeof(int) * rest_rows.size());
     if (rest_out) rest_out->swap(rest_rows);
+    plan->rg_host = rh;
+    crp_panel_build(plan);
 }
 
 void crp_rowgroup_destroy(crp_spmm_plan *plan)
 {
     crp_rowgroup *rg = &plan->rg;
+    crp_panel_destroy(plan);
+    delete plan->rg_host;
+    plan->rg_host = NULL;
     if (rg->d_grow) CRP_CUDA_CHECK(cudaFree(rg->d_grow));
     if (rg->d_gptr) CRP_CUDA_CHECK(cudaFree(rg->d_gptr));
     if (rg->d_bcol) CRP_CUDA_CHECK(cudaFree(rg->d_bcol));
@@ -233,51 +191,9 @@ __device__ __forceinline__ void load_block_vals(const T *__restrict__ p, T (&a)[
     }
 }
 
-// one stage of the software pipeline: NB blocks' worth of B-row segments and values
-template <typename T, int VEC, int R, int U, int NB>
-struct rg_stage
-{
-    T x[NB][U][VEC];
-    T a[NB][R];
-};
-
-template <typename T, int VEC, int R, int U, int NB>
-__device__ __forceinline__ void rg_load_stage(
-    rg_stage<T, VEC, R, U, NB> &st, const int (&c)[NB], const int p, const T *__restrict__ bval, const int (&voff)[U],
-    const T *__restrict__ X0, const size_t ldx0, const int x0_rows, const T *__restrict__ X1, const size_t ldx1
-)
-{
-    #pragma unroll
-    for (int q = 0; q < NB; q++)
-    {
-        const T *xr = (c[q] < x0_rows) ? X0 + (size_t) c[q] * ldx0 : X1 + (size_t) (c[q] - x0_rows) * ldx1;
-        #pragma unroll
-        for (int u = 0; u < U; u++)
-        {
-            if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], st.x[q][u]);
-            else { for (int e = 0; e < VEC; e++) st.x[q][u][e] = (T) 0; }
-        }
-        load_block_vals<T, R>(bval + (size_t) (p + q) * R, st.a[q]);
-    }
-}
-
-template <typename T, int VEC, int R, int U, int NB>
-__device__ __forceinline__ void rg_fma_stage(const rg_stage<T, VEC, R, U, NB> &st, T (&acc)[R][U][VEC])
-{
-    #pragma unroll
-    for (int q = 0; q < NB; q++)
-        #pragma unroll
-        for (int r = 0; r < R; r++)
-            #pragma unroll
-            for (int u = 0; u < U; u++)
-                #pragma unroll
-                for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(st.a[q][r], st.x[q][u][e], acc[r][u][e]);
-}
-
-// PIPE = 1: the loads of the next NB blocks are issued before the FMAs of the current ones (register
-// double buffering).  PF > 0: the B rows of the blocks PF positions ahead are prefetched into L1
-// (CCTL.E.PF1, one 128-byte line per lane), which keeps gathers in flight without holding registers.
-template <typename T, int VEC, int R, int LPR, int U, int NB, int PIPE, int PF, int BS>
+// Register-only variant for narrow dense matrices (a group is owned by LPR < 32 lanes): NB blocks in flight per step,
+// the column indices of the next step prefetched.  beta == 0 only (the caller routes beta != 0 to the staged variant).
+template <typename T, int VEC, int R, int LPR, int U, int NB, int BS>
 __global__ void __launch_bounds__(BS) spmm_rowgroup_kernel(
     const int ngroups, const int *__restrict__ grow, const int *__restrict__ gptr,
     const int *__restrict__ bcol, const T *__restrict__ bval,
@@ -308,82 +224,37 @@ __global__ void __launch_bounds__(BS) spmm_rowgroup_kernel(
             #pragma unroll
             for (int e = 0; e < VEC; e++) acc[r][u][e] = (T) 0;
 
-    // L1 prefetch: lane l covers bytes [128 l, 128 l + 128) of the CTA's column chunk of a B row
-    constexpr int CHUNK_BYTES = LPR * U * VEC * (int) sizeof(T);
-    const int pf_off = (v0 * VEC * (int) sizeof(T)) + l * 128;
-    const bool pf_lane = (PF > 0) && (l * 128 < CHUNK_BYTES) && (v0 * VEC + l * (128 / (int) sizeof(T)) < nv * VEC);
-    auto prefetch_row = [&](const int pp) {
-        if (PF > 0 && pp < p_end && pf_lane)
-        {
-            const int c = __ldg(bcol + pp);
-            const char *xr = (c < x0_rows) ? (const char *) (X0 + (size_t) c * ldx0) : (const char *) (X1 + (size_t) (c - x0_rows) * ldx1);
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(xr + pf_off));
-        }
-    };
-    if (PF > 0)
-    {
-        #pragma unroll 1
-        for (int d = 0; d < PF; d++) prefetch_row(p + d);
-    }
-
-    typedef rg_stage<T, VEC, R, U, NB> stage_t;
     int cn[NB];
     #pragma unroll
     for (int q = 0; q < NB; q++) cn[q] = (p + q < p_end) ? __ldg(bcol + p + q) : 0;
-
-    if (PIPE == 0)
+    for (; p + NB <= p_end; p += NB)
     {
-        for (; p + NB <= p_end; p += NB)
+        int c[NB];
+        #pragma unroll
+        for (int q = 0; q < NB; q++) c[q] = cn[q];
+        #pragma unroll
+        for (int q = 0; q < NB; q++) cn[q] = (p + NB + q < p_end) ? __ldg(bcol + p + NB + q) : 0;
+        T x[NB][U][VEC], a[NB][R];
+        #pragma unroll
+        for (int q = 0; q < NB; q++)
         {
-            int c[NB];
+            const T *xr = (c[q] < x0_rows) ? X0 + (size_t) c[q] * ldx0 : X1 + (size_t) (c[q] - x0_rows) * ldx1;
             #pragma unroll
-            for (int q = 0; q < NB; q++) c[q] = cn[q];
-            #pragma unroll
-            for (int q = 0; q < NB; q++) cn[q] = (p + NB + q < p_end) ? __ldg(bcol + p + NB + q) : 0;
-            #pragma unroll
-            for (int q = 0; q < NB; q++) prefetch_row(p + PF + q);
-            stage_t st;
-            rg_load_stage<T, VEC, R, U, NB>(st, c, p, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
-            rg_fma_stage<T, VEC, R, U, NB>(st, acc);
-        }
-    } else {
-        stage_t sa, sb;
-        bool have_a = false;
-        if (p + NB <= p_end)
-        {
-            rg_load_stage<T, VEC, R, U, NB>(sa, cn, p, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
-            have_a = true;
-            #pragma unroll
-            for (int q = 0; q < NB; q++) cn[q] = (p + NB + q < p_end) ? __ldg(bcol + p + NB + q) : 0;
-        }
-        // invariant: sa holds blocks [p, p + NB), cn the columns of [p + NB, p + 2 NB)
-        while (have_a)
-        {
-            const bool next_b = (p + 2 * NB <= p_end);
-            if (next_b)
+            for (int u = 0; u < U; u++)
             {
-                rg_load_stage<T, VEC, R, U, NB>(sb, cn, p + NB, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
-                #pragma unroll
-                for (int q = 0; q < NB; q++) cn[q] = (p + 2 * NB + q < p_end) ? __ldg(bcol + p + 2 * NB + q) : 0;
+                if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], x[q][u]);
+                else { for (int e = 0; e < VEC; e++) x[q][u][e] = (T) 0; }
             }
-            #pragma unroll
-            for (int q = 0; q < NB; q++) prefetch_row(p + PF + q);
-            rg_fma_stage<T, VEC, R, U, NB>(sa, acc);
-            p += NB;
-            if (!next_b) break;
-            const bool next_a = (p + 2 * NB <= p_end);
-            if (next_a)
-            {
-                rg_load_stage<T, VEC, R, U, NB>(sa, cn, p + NB, bval, voff, X0, ldx0, x0_rows, X1, ldx1);
-                #pragma unroll
-                for (int q = 0; q < NB; q++) cn[q] = (p + 2 * NB + q < p_end) ? __ldg(bcol + p + 2 * NB + q) : 0;
-            }
-            #pragma unroll
-            for (int q = 0; q < NB; q++) prefetch_row(p + PF + q);
-            rg_fma_stage<T, VEC, R, U, NB>(sb, acc);
-            p += NB;
-            have_a = next_a;
+            load_block_vals<T, R>(bval + (size_t) (p + q) * R, a[q]);
         }
+        #pragma unroll
+        for (int q = 0; q < NB; q++)
+            #pragma unroll
+            for (int r = 0; r < R; r++)
+                #pragma unroll
+                for (int u = 0; u < U; u++)
+                    #pragma unroll
+                    for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[q][r], x[q][u][e], acc[r][u][e]);
     }
     // fewer than NB blocks left; cn[] holds their columns
     #pragma unroll
@@ -427,12 +298,11 @@ __global__ void __launch_bounds__(BS) spmm_rowgroup_kernel(
 }
 
 // ---- variant with the block values and columns staged through shared memory ("sv") ----
-// In the kernel above every iteration waits for the block values: they stream from HBM (first
-// touch, no reuse), so each NB-block step pays a full DRAM round trip (~1400 cycles, ncu:
-// long_scoreboard 2.9 of 4.0 stall slots) before its FMAs.  Here a warp copies the values and
-// columns of the next CB blocks of its group into its private shared-memory ring with cp.async
-// (LDGSTS, no registers held) while it works on the current CB blocks, and reads them back with
-// broadcast LDS (29 cycles).  Only the B-row gathers remain long-latency loads.
+// A warp owns one group.  It copies the values and columns of the next CB blocks of its group into its private
+// shared-memory ring with cp.async (LDGSTS, no registers held) while it works on the current CB blocks, and reads
+// them back with broadcast LDS; only the B-row gathers remain long-latency loads.  Round-1 kernel of the headline
+// configuration (0.42 ms); since round 2 the fallback of spmm_panel.cu for operands the bulk copies cannot take
+// (unaligned pointers / leading dimensions, n < 64).
 __device__ __forceinline__ void cp_async_bytes16(void *smem, const void *gmem)
 {
     const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
@@ -471,7 +341,7 @@ __device__ __forceinline__ void lds_block_vals(const T *p, T (&a)[R])
     }
 }
 
-template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE, int PF, int MINB>
+template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int MINB>
 __global__ void __launch_bounds__(BS, MINB) spmm_rowgroup_sv_kernel(
     const int ngroups, const int *__restrict__ grow, const int *__restrict__ gptr,
     const int *__restrict__ bcol, const T *__restrict__ bval,
@@ -520,96 +390,9 @@ __global__ void __launch_bounds__(BS, MINB) spmm_rowgroup_sv_kernel(
         cp_async_commit();
     };
 
-    if constexpr (PIPE == 2)
-    {
-        // Rolling prefetch: the registers of an (block, column-group) slot are reloaded with the data of the
-        // same slot NB blocks ahead right after the FMAs that consumed them, so the gathers of the next step
-        // are in flight during the whole FMA phase of the current one - without a second set of registers.
-        static_assert(CB % NB == 0, "chunk size must be a multiple of the blocks per step");
-        const int total = p_end - p_beg;
-        const int nchunk = (total + CB - 1) / CB;
-        stage(0, p_beg, min(CB, total));
-        cp_async_wait_all();
-        __syncwarp();
-        if (nchunk > 1) stage(1, p_beg + CB, min(CB, total - CB));
-        auto col_at = [&](const int jj) -> int { return s_col[wib][(jj / CB) & 1][jj % CB]; };
-        auto row_at = [&](const int jj) -> const T * {
-            const int c = col_at(jj);
-            return (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
-        };
-        T x[NB][U][VEC];
-        const int nfull = total - total % NB;
-        if (nfull > 0)
-        {
-            #pragma unroll
-            for (int q = 0; q < NB; q++)
-            {
-                const T *xr = row_at(q);
-                #pragma unroll
-                for (int u = 0; u < U; u++)
-                {
-                    if (voff[u] >= 0) xload<T, VEC>::ld(xr + voff[u], x[q][u]);
-                    else { for (int e = 0; e < VEC; e++) x[q][u][e] = (T) 0; }
-                }
-            }
-        }
-        for (int j = 0; j < nfull; j += NB)
-        {
-            const int chunk = j / CB;
-            const bool last_of_chunk = ((j % CB) == CB - NB);
-            if (last_of_chunk && chunk + 1 < nchunk) { cp_async_wait_all(); __syncwarp(); }     // next chunk readable for the look-ahead
-            const T *sv = reinterpret_cast<const T *>(&s_val[wib][chunk & 1][0]);
-            #pragma unroll
-            for (int q = 0; q < NB; q++)
-            {
-                T a[R];
-                lds_block_vals<T, R>(sv + (size_t) ((j % CB) + q) * R, a);
-                const int jn = j + NB + q;                  // the block that takes this slot next
-                const T *xn = row_at(jn < nfull ? jn : nfull - 1);
-                #pragma unroll
-                for (int u = 0; u < U; u++)
-                {
-                    #pragma unroll
-                    for (int r = 0; r < R; r++)
-                        #pragma unroll
-                        for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], x[q][u][e], acc[r][u][e]);
-                    if (voff[u] >= 0) xload<T, VEC>::ld(xn + voff[u], x[q][u]);
-                }
-            }
-            if (last_of_chunk)
-            {
-                __syncwarp();                               // everybody is done with this chunk's buffer
-                if (chunk + 2 < nchunk) stage(chunk & 1, p_beg + (chunk + 2) * CB, min(CB, total - (chunk + 2) * CB));
-            }
-        }
-        if (nfull < total)                                  // fewer than NB blocks left
-        {
-            const int chunk = nfull / CB;
-            if (nfull > 0 && (nfull % CB) == 0) { cp_async_wait_all(); __syncwarp(); }
-            const T *sv = reinterpret_cast<const T *>(&s_val[wib][chunk & 1][0]);
-            for (int j = nfull; j < total; j++)
-            {
-                const T *xr = row_at(j);
-                T a[R];
-                lds_block_vals<T, R>(sv + (size_t) (j % CB) * R, a);
-                #pragma unroll
-                for (int u = 0; u < U; u++)
-                {
-                    if (voff[u] < 0) continue;
-                    T xx[VEC];
-                    xload<T, VEC>::ld(xr + voff[u], xx);
-                    #pragma unroll
-                    for (int r = 0; r < R; r++)
-                        #pragma unroll
-                        for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], xx[e], acc[r][u][e]);
-                }
-            }
-        }
-    }
-
     int buf = 0;
-    if (PIPE != 2) stage(0, p_beg, min(CB, p_end - p_beg));
-    for (int pc = p_beg; PIPE != 2 && pc < p_end; pc += CB, buf ^= 1)
+    stage(0, p_beg, min(CB, p_end - p_beg));
+    for (int pc = p_beg; pc < p_end; pc += CB, buf ^= 1)
     {
         const int nb = min(CB, p_end - pc);
         cp_async_wait_all();
@@ -618,15 +401,14 @@ __global__ void __launch_bounds__(BS, MINB) spmm_rowgroup_sv_kernel(
         const T *sv = reinterpret_cast<const T *>(&s_val[wib][buf][0]);
         const int *sc = &s_col[wib][buf][0];
         int j = 0;
-        auto row_of = [&](const int jj) -> const T * {
-            const int c = sc[jj];
-            return (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
-        };
-        auto load_x = [&](const int jj, T (&x)[NB][U][VEC]) {
+        for (; j + NB <= nb; j += NB)
+        {
+            T x[NB][U][VEC];
             #pragma unroll
             for (int q = 0; q < NB; q++)
             {
-                const T *xr = row_of(jj + q);
+                const int c = sc[j + q];
+                const T *xr = (c < x0_rows) ? X0 + (size_t) c * ldx0 : X1 + (size_t) (c - x0_rows) * ldx1;
                 #pragma unroll
                 for (int u = 0; u < U; u++)
                 {
@@ -634,54 +416,17 @@ __global__ void __launch_bounds__(BS, MINB) spmm_rowgroup_sv_kernel(
                     else { for (int e = 0; e < VEC; e++) x[q][u][e] = (T) 0; }
                 }
             }
-        };
-        auto fma_x = [&](const int jj, const T (&x)[NB][U][VEC]) {
             #pragma unroll
             for (int q = 0; q < NB; q++)
             {
                 T a[R];
-                lds_block_vals<T, R>(sv + (size_t) (jj + q) * R, a);
+                lds_block_vals<T, R>(sv + (size_t) (j + q) * R, a);
                 #pragma unroll
                 for (int r = 0; r < R; r++)
                     #pragma unroll
                     for (int u = 0; u < U; u++)
                         #pragma unroll
                         for (int e = 0; e < VEC; e++) acc[r][u][e] = fma(a[r], x[q][u][e], acc[r][u][e]);
-            }
-        };
-        // L1 prefetch of the B rows PF blocks ahead (lane l covers the l-th 128-byte line of the column chunk)
-        constexpr int CHUNK_BYTES = 32 * U * VEC * (int) sizeof(T);
-        const bool pf_lane = (PF > 0) && (lane * 128 < CHUNK_BYTES) && (v0 * VEC + lane * (128 / (int) sizeof(T)) < nv * VEC);
-        auto prefetch = [&](const int jj) {
-            if (PF > 0 && jj < nb && pf_lane)
-                asm volatile("prefetch.global.L1 [%0];" :: "l"((const char *) row_of(jj) + (size_t) v0 * VEC * sizeof(T) + lane * 128));
-        };
-        if (PF > 0) { for (int d = 0; d < PF; d++) prefetch(d); }
-        if (PIPE == 0)
-        {
-            for (; j + NB <= nb; j += NB)
-            {
-                T x[NB][U][VEC];
-                #pragma unroll
-                for (int q = 0; q < NB; q++) prefetch(j + PF + q);
-                load_x(j, x);
-                fma_x(j, x);
-            }
-        } else {
-            T xa[NB][U][VEC], xb[NB][U][VEC];
-            if (j + NB <= nb) load_x(j, xa);
-            while (j + NB <= nb)
-            {
-                const bool nb1 = (j + 2 * NB <= nb);
-                if (nb1) load_x(j + NB, xb);
-                fma_x(j, xa);
-                j += NB;
-                if (!nb1) break;
-                const bool nb2 = (j + 2 * NB <= nb);
-                if (nb2) load_x(j + NB, xa);
-                fma_x(j, xb);
-                j += NB;
-                if (!nb2) break;
             }
         }
         for (; j < nb; j++)
@@ -731,18 +476,18 @@ __global__ void __launch_bounds__(BS, MINB) spmm_rowgroup_sv_kernel(
 }
 
 // MINB: 128-thread CTAs are meant to run 3 per SM (<= 170 registers); without the bound ptxas spends 188 and drops to 2
-template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int PIPE = 0, int PF = 0, int MINB = (BS == 128 ? 3 : 1)>
+template <typename T, int VEC, int R, int U, int NB, int BS, int CB, int MINB = (BS == 128 ? 3 : 1)>
 static void rg_launch_sv(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s)
 {
     const unsigned blocks = (unsigned) ((rg->ngroups + BS / 32 - 1) / (BS / 32));
     const unsigned chunks = (unsigned) ((nv + 32 * U - 1) / (32 * U));
     if (blocks == 0) return;
-    spmm_rowgroup_sv_kernel<T, VEC, R, U, NB, BS, CB, PIPE, PF, MINB><<<dim3(blocks, chunks), BS, 0, s>>>(
+    spmm_rowgroup_sv_kernel<T, VEC, R, U, NB, BS, CB, MINB><<<dim3(blocks, chunks), BS, 0, s>>>(
         rg->ngroups, rg->d_grow, rg->d_gptr, rg->d_bcol, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc);
     CRP_LAUNCH_CHECK();
 }
 
-template <typename T, int VEC, int R, int LPR, int U, int NB = 2, int PIPE = 0, int PF = 0, int BS = 256>
+template <typename T, int VEC, int R, int LPR, int U, int NB = 2, int BS = 256>
 static void rg_launch_one(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
 {
     constexpr int GW = 32 / LPR;
@@ -750,96 +495,15 @@ static void rg_launch_one(const crp_rowgroup *rg, const T *bval, int nv, const T
     const unsigned blocks = (unsigned) ((warps + BS / 32 - 1) / (BS / 32));
     const unsigned chunks = (unsigned) ((nv + LPR * U - 1) / (LPR * U));
     if (blocks == 0) return;
-    spmm_rowgroup_kernel<T, VEC, R, LPR, U, NB, PIPE, PF, BS><<<dim3(blocks, chunks), BS, 0, s>>>(
+    spmm_rowgroup_kernel<T, VEC, R, LPR, U, NB, BS><<<dim3(blocks, chunks), BS, 0, s>>>(
         rg->ngroups, rg->d_grow, rg->d_gptr, rg->d_bcol, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc);
     CRP_LAUNCH_CHECK();
-}
-
-bool crp_launch_rowgroup_x(
-    const int cfg, const crp_rowgroup *rg, const double *bval, const int n, const double *X0, const size_t ldx0,
-    const double *X1, const double alpha, const double beta, double *C, const size_t ldc, cudaStream_t s
-);
-
-// development switch (CRP_SPMM_RG_CFG = index): fp64, 128-bit, R = 6, full-warp groups only.
-// Indices 0..49 are the configurations measured in round 1 (compiled only with -DCRP_DEV_SWEEP); 60.. are the lean variants of
-// spmm_rowgroup_x.cu.  Without the variable, or for an index that is not compiled in, the shipped kernel runs.
-template <typename T, int VEC, int R>
-static bool rg_launch_experiment(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T *C, size_t ldc, cudaStream_t s)
-{
-    if constexpr (sizeof(T) == 8 && VEC == 2 && R == 6)
-    {
-        const char *e = getenv("CRP_SPMM_RG_CFG");
-        if (e == NULL || nv < 128) return false;
-        if (atoi(e) >= 60) return crp_launch_rowgroup_x(atoi(e), rg, bval, nv * VEC, X0, ldx0, X1, alpha, 0.0, C, ldc, s);   // spmm_rowgroup_x.cu
-#ifdef CRP_DEV_SWEEP     /* the round-1 sweep (profiles/kbench*.log): build with CRP_NVCC_EXTRA=-DCRP_DEV_SWEEP to get these ~40 instantiations */
-#define CRP_RGX(U, NB, PIPE, PF, BS) rg_launch_one<T, VEC, R, 32, U, NB, PIPE, PF, BS>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s); return true
-        switch (atoi(e))
-        {
-            case 0:  CRP_RGX(4, 2, 0, 0, 256);
-            case 1:  CRP_RGX(4, 2, 0, 0, 128);
-            case 2:  CRP_RGX(2, 2, 0, 0, 256);
-            case 3:  CRP_RGX(2, 4, 0, 0, 256);
-            case 4:  CRP_RGX(4, 1, 1, 0, 128);
-            case 5:  CRP_RGX(4, 2, 0, 8, 128);
-            case 6:  CRP_RGX(2, 2, 1, 0, 128);
-            case 7:  CRP_RGX(2, 2, 0, 8, 256);
-            case 8:  CRP_RGX(1, 4, 0, 0, 256);
-            case 9:  CRP_RGX(4, 1, 1, 8, 128);
-            case 10: CRP_RGX(2, 4, 0, 16, 256);
-            case 11: CRP_RGX(1, 4, 0, 16, 256);
-            case 12: CRP_RGX(4, 1, 0, 8, 128);
-            case 13: CRP_RGX(2, 1, 1, 0, 256);
-#define CRP_RGSV(U, NB, BS, CB) rg_launch_sv<T, VEC, R, U, NB, BS, CB>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, (T) 0, C, ldc, s); return true
-            case 20: CRP_RGSV(4, 2, 128, 32);
-            case 21: CRP_RGSV(4, 2, 256, 32);
-            case 22: CRP_RGSV(4, 1, 128, 32);
-            case 23: CRP_RGSV(4, 4, 128, 32);
-            case 24: CRP_RGSV(2, 2, 128, 32);
-            case 25: CRP_RGSV(2, 4, 128, 32);
-            case 26: CRP_RGSV(2, 4, 256, 32);
-            case 27: CRP_RGSV(4, 2, 128, 64);
-            case 28: CRP_RGSV(4, 3, 128, 32);
-            case 29: CRP_RGSV(1, 4, 256, 32);
-#define CRP_RGSV2(U, NB, BS, CB, PIPE, PF) rg_launch_sv<T, VEC, R, U, NB, BS, CB, PIPE, PF>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, (T) 0, C, ldc, s); return true
-            case 30: CRP_RGSV2(4, 1, 128, 32, 1, 0);
-            case 31: CRP_RGSV2(4, 2, 128, 32, 1, 0);
-            case 32: CRP_RGSV2(2, 2, 128, 32, 1, 0);
-            case 33: CRP_RGSV2(4, 2, 128, 32, 0, 4);
-            case 34: CRP_RGSV2(4, 2, 128, 32, 0, 8);
-            case 35: CRP_RGSV2(2, 2, 128, 32, 0, 8);
-            case 36: CRP_RGSV2(4, 1, 128, 32, 0, 8);
-            case 37: CRP_RGSV2(2, 1, 128, 32, 1, 0);
-            case 38: CRP_RGSV2(4, 2, 64, 32, 0, 0);
-            case 39: CRP_RGSV2(4, 2, 96, 32, 0, 0);
-            case 40: CRP_RGSV2(4, 2, 128, 32, 2, 0);
-            case 41: CRP_RGSV2(4, 1, 128, 32, 2, 0);
-            case 42: CRP_RGSV2(2, 2, 128, 32, 2, 0);
-            case 43: CRP_RGSV2(2, 4, 128, 32, 2, 0);
-            case 44: CRP_RGSV2(4, 4, 128, 32, 2, 0);
-            case 45: CRP_RGSV2(2, 2, 256, 32, 2, 0);
-#define CRP_RGSV3(U, NB, BS, CB, MINB) rg_launch_sv<T, VEC, R, U, NB, BS, CB, 0, 0, MINB>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, (T) 0, C, ldc, s); return true
-            case 46: CRP_RGSV3(4, 2, 128, 32, 4);
-            case 47: CRP_RGSV3(4, 1, 128, 32, 4);
-            case 48: CRP_RGSV3(4, 2, 64, 32, 7);
-            case 49: CRP_RGSV3(4, 1, 64, 32, 8);
-#undef CRP_RGSV3
-#undef CRP_RGSV2
-#undef CRP_RGSV
-            default: return false;
-        }
-#undef CRP_RGX
-#endif
-    }
-    return false;
 }
 
 template <typename T, int VEC, int R>
 static void rg_launch_R(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s)
 {
-    if (beta == (T) 0 && rg_launch_experiment<T, VEC, R>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)) return;
     constexpr int UMAX = (R * VEC * (int) sizeof(T) <= 6 * 16) ? 4 : 2;       // keep the accumulator tile <= 96 registers
-    // Full-warp groups: values / columns staged through shared memory (measured on the pwtk-shaped
-    // n = 256 fp64 case: 0.60 -> 0.42 ms); 128-thread CTAs so that 168 registers still give 12 warps per SM.
 #define CRP_SV(U, NB, BS) rg_launch_sv<T, VEC, R, U, NB, BS, 32>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, beta, C, ldc, s)
 #define CRP_RG(LPR, U) rg_launch_one<T, VEC, R, LPR, U>(rg, bval, nv, X0, ldx0, x0_rows, X1, ldx1, alpha, C, ldc, s)
     if (nv >= 128 && UMAX >= 4) CRP_SV(4, 2, 128);

@@ -30,7 +30,11 @@ int crp_opt_plan_only(void)
 int crp_opt_pin_host(void)
 {
     static int v = -1;
-    if (v < 0) GET_ENV_INT_VAR(v, "CRP_SPMM_PIN_HOST", "pin_host", 1, 0, 1, 0);
+    /* OPT-IN (default 0): a cudaHostRegister registration outlives the caller's buffer - if the caller frees B or C and a
+     * later malloc returns the same address, CUDA would still DMA from / to the old physical pages.  Callers that keep their
+     * buffers for the life of the engine (the reference drivers do) may set CRP_SPMM_PIN_HOST=1; registrations are dropped
+     * by crp_unpin_host_all() and whenever an engine is freed. */
+    if (v < 0) GET_ENV_INT_VAR(v, "CRP_SPMM_PIN_HOST", "pin_host", 0, 0, 1, 0);
     return v;
 }
 
@@ -88,6 +92,12 @@ void crp_pin_host_range(const void *ptr, size_t bytes)
         g_pins[g_npin].bytes = bytes;
         g_npin++;
     }
+}
+
+void crp_unpin_host_all(void)
+{
+    for (int i = 0; i < g_npin; i++) crp_cuda_host_unregister(g_pins[i].ptr);
+    g_npin = 0;
 }
 
 int *crp_comm_ranks_in_parent(MPI_Comm sub, MPI_Comm parent)

@@ -75,6 +75,7 @@ struct crp_rp_dev
     double  ring_host_t1[CRP_RP_RING];
     void    *mark[CRP_RP_RING][CRP_RP_NEV]; /* event that closes each phase (a phase without work reuses the previous one) */
     int     ring_head, ring_count;
+    long long n_folded;         /* execs whose event times have been folded into the statistics      */
     double  t_h2d, t_d2h;       /* staging of host B / C (seconds, device time)                      */
     int     staged;             /* 1: exchange through pinned host memory + MPI (ranks share a GPU)  */
     /* peer-memory transport (CRP_SPMM_TRANSPORT=2): rows are stored straight into the peers' receive buffers */

@@ -186,6 +186,7 @@ static void rp_build_plan(
 #define CRP_DEFAULT_TRANSPORT 2
 #endif
 enum { CRP_P2P_HDR = 1024 };
+#define CRP_P2P_TIMEOUT_S 20.0
 
 /*
  * Peer-memory transport: every rank exports one allocation (arrival flags + two receive halves) with
@@ -482,6 +483,7 @@ void rp_spmm_free(rp_spmm_p *rp_spmm)
     rp_spmm_p rp = *rp_spmm;
     if (rp == NULL) return;
     rp_free_device_state(rp);
+    crp_unpin_host_all();           /* registrations of caller buffers never outlive the engine that made them */
     free(rp->A_rowptr);
     free(rp->A_colidx);
     free(rp->A_val);
@@ -496,18 +498,33 @@ void rp_spmm_free(rp_spmm_p *rp_spmm)
     *rp_spmm = NULL;
 }
 
-/* Fold the events of finished execs into the statistics.  wait = 0: only those whose events
- * have completed (never stalls the host); wait = 1: all of them (synchronises). */
-static void rp_collect(rp_spmm_p rp, const int wait)
+/* A peer-memory exec whose wait for a neighbour timed out has produced garbage: never let that pass silently,
+ * whatever the blocking mode (the flag is pinned host memory written by the wait kernel / the SpMM kernel). */
+static void rp_check_p2p_error(struct crp_rp_dev *d)
+{
+    if (d != NULL && d->p2p && d->h_err != NULL && *(volatile int *) d->h_err)
+    {
+        fprintf(stderr, "[FATAL] rp_spmm_exec: a neighbour's B rows did not arrive within %g s (peer-memory transport)\n", CRP_P2P_TIMEOUT_S);
+        fflush(stderr);
+        abort();
+    }
+}
+
+/* Fold the events of finished execs into the statistics.  mode 0: only those whose events have completed
+ * (never stalls the host); 1: all of them (synchronises); 2: make room in the ring - wait for the oldest
+ * exec only, then fold whatever else has completed. */
+static void rp_collect(rp_spmm_p rp, const int mode)
 {
     struct crp_rp_dev *d = (struct crp_rp_dev *) rp->dev;
     if (d == NULL) return;
+    int wait = (mode != 0);
     while (d->ring_count > 0)
     {
         const int k = (d->ring_head - d->ring_count + CRP_RP_RING) % CRP_RP_RING;      /* oldest */
         void **ev = d->mark[k];
         if (wait) crp_cuda_event_sync(ev[CRP_EV_END]);
         else if (!crp_cuda_event_done(ev[CRP_EV_END])) break;
+        if (mode == 2) wait = 0;
         rp->t_pack += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_B_IN],   ev[CRP_EV_PACKED]);
         rp->t_a2a  += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_PACKED], ev[CRP_EV_XCHG]);
         if (d->ring_overlap[k])     /* own-rows product (concurrent with the exchange) + received-rows product */
@@ -520,7 +537,9 @@ static void rp_collect(rp_spmm_p rp, const int wait)
         if (d->ring_host_t1[k] > 0.0) rp->t_exec += d->ring_host_t1[k] - d->ring_host_t0[k];
         else rp->t_exec += 1e-3 * crp_cuda_event_elapsed_ms(ev[CRP_EV_START], ev[CRP_EV_END]);
         d->ring_count--;
+        d->n_folded++;
     }
+    rp_check_p2p_error(d);
 }
 
 /* the exchange of packed rows: device send buffer -> device receive buffer */
@@ -579,7 +598,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         fflush(stderr);
         abort();
     }
-    rp_collect(rp, d->ring_count == CRP_RP_RING);
+    rp_collect(rp, d->ring_count == CRP_RP_RING ? 2 : 0);
     const double host_t0 = get_wtime_sec();
     void **ev = d->ev[d->ring_head];
     void **mark = d->mark[d->ring_head];
@@ -648,7 +667,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         if (d->n_send_rows > 0) crp_cuda_put_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, (void *const *) d->d_dst_rows[half], cs);
         CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0, cs);
         crp_cuda_signal_peers((unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, cs);
-        crp_cuda_wait_flags((const unsigned int *) d->p2p_mem, d->d_wait_idx, d->n_wait, d->epoch, 20.0, d->h_err, cs);
+        crp_cuda_wait_flags((const unsigned int *) d->p2p_mem, d->d_wait_idx, d->n_wait, d->epoch, CRP_P2P_TIMEOUT_S, d->h_err, cs);
         CRP_MARK_ON(CRP_EV_XCHG, overlap || d->n_flag > 0, cs);
         X1 = (const char *) d->p2p_mem + CRP_P2P_HDR + (size_t) half * d->p2p_half_bytes;
     } else {
@@ -720,12 +739,6 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     {
         crp_cuda_event_sync(mark[CRP_EV_END]);
         d->ring_host_t1[k] = get_wtime_sec();
-        if (d->p2p && *d->h_err)
-        {
-            fprintf(stderr, "[FATAL] rp_spmm_exec: a neighbour's B rows did not arrive within 20 s (peer-memory transport)\n");
-            fflush(stderr);
-            abort();
-        }
         rp_collect(rp, 1);
     }
 }
@@ -752,7 +765,18 @@ void rp_spmm_set_kernel(rp_spmm_p rp, const char *name)
     crp_cuda_spmm_set_variant(((struct crp_rp_dev *) rp->dev)->plan, name);
 }
 
+void rp_spmm_plan_info(rp_spmm_p rp, long long out[12])
+{
+    for (int i = 0; i < 12; i++) out[i] = 0;
+    if (rp != NULL && rp->dev != NULL) crp_cuda_spmm_plan_info(((struct crp_rp_dev *) rp->dev)->plan, out);
+}
+
 int rp_spmm_is_plan_only(rp_spmm_p rp) { return (rp != NULL && rp->dev == NULL) ? 1 : 0; }
+
+void rp_spmm_sync_stats(rp_spmm_p rp)
+{
+    if (rp != NULL && rp->dev != NULL) rp_collect(rp, 1);
+}
 
 void rp_spmm_device_times(rp_spmm_p rp, double *t_h2d, double *t_d2h)
 {

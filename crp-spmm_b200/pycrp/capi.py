@@ -206,6 +206,12 @@ def load():
     L.crp_cuda_spmm_last_kernel.restype = C.c_char_p
     L.crp_cuda_spmm_set_variant.argtypes = [vp, C.c_char_p]
     L.crp_cuda_csr_spmm_host.argtypes = [i, i, i, d, i, vp, vp, vp, vp, i, d, vp, i]
+    L.crp_cuda_spmm_plan_info.argtypes = [vp, vp]
+    L.crp_cuda_measure_dfma_tflops.restype = d
+    L.rp_spmm_sync_stats.argtypes = [C.POINTER(RowparaSpmm)]
+    L.rp_spmm_plan_info.argtypes = [C.POINTER(RowparaSpmm), vp]
+    L.crp_nccl_world_nranks.restype = i
+    L.crp_nccl_version.restype = i
     L.crp_set_stream.argtypes = [vp]
     L.crp_set_blocking.argtypes = [i]
     L.crp_kernel_launch_count.restype = C.c_ulonglong

@@ -126,10 +126,33 @@ void crp_cuda_spmm_exec(
     const void *X0, const int ldx0, const void *X1, const int ldx1,
     const double beta, void *C, const int ldc, void *stream
 );
+/* Same product, for the peer-memory transport of rp_spmm_exec (successor of the MPI_Waitall at reference
+ * src/rowpara_spmm.c:301): X1 is a receive buffer that the neighbours' GPUs fill with NVLink stores; the
+ * kernel waits for flags_d[wait_idx_d[j]] >= epoch (j < nwait) itself, and - when the plan has a wait map -
+ * only right before the first piece of work that reads a row of that neighbour, so everything that needs
+ * the rank's own B rows only runs while the exchange is still in flight.  nwait == 0: plain exec.
+ * On timeout *err (pinned host memory) is set to 1. */
+void crp_cuda_spmm_exec_wait(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
+    const void *X0, const int ldx0, const void *X1, const int ldx1,
+    const double beta, void *C, const int ldc,
+    const unsigned int *flags_d, const int *wait_idx_d, const int nwait, const unsigned int epoch, const double timeout_s, int *err,
+    void *stream
+);
+/* wait map: rows [recv_off[j], recv_off[j + 1]) of X1 are written by the neighbour of wait slot j (nslot <= 32) */
+void crp_cuda_spmm_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *recv_off);
 /* name of the kernel variant the last crp_cuda_spmm_exec on this plan launched (static string) */
 const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan);
-/* force a kernel variant for experiments: "auto", "rowsplit", "rowgroup", "mergepath" */
+/* force a kernel variant for experiments: "auto", "rowsplit", "rowgroup", "panel", "mergepath" */
 void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name);
+
+/* what the plan holds: out[0] group size R (1: none), [1] groups, [2] R x 1 blocks, [3] rows left to the row-split kernel,
+ * [4] their nonzeros, [5] panel tiles, [6] panel chunks, [7] B rows staged per pass (sum of the tiles' unions), [8] 1 if all groups
+ * are exact, [9] long rows cut into segments, [10] nnz, [11] merge-path chunks */
+void crp_cuda_spmm_plan_info(const crp_spmm_plan *plan, long long out[12]);
+
+/* measured fp64 FMA throughput of the current device in TFLOP/s (pure DFMA issue; for the fp64 roofline of bench.py) */
+double crp_cuda_measure_dfma_tflops(void);
 
 /* Host-only view of the plan-time kernel selection (needs no device): the row-group size R (1 = row-split kernel only), the
  * alignment of the first group, the number of R x 1 blocks, and how many rows are long enough to be cut into segments. */

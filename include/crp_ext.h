@@ -29,6 +29,10 @@ void crp_set_blocking(const int blocking);
 unsigned long long crp_kernel_launch_count(void);
 unsigned long long crp_nccl_group_count(void);
 
+/* Size of the NCCL communicator spanning MPI_COMM_WORLD (created on first use; collective), NCCL's version code. */
+int crp_nccl_world_nranks(void);
+int crp_nccl_version(void);
+
 /* Name of the local-SpMM kernel variant the engine's last exec launched. */
 const char *rp_spmm_kernel_name(rp_spmm_p rp_spmm);
 /* Force a variant ("auto", "rowsplit", "rowgroup", "mergepath") for experiments. */
@@ -36,6 +40,18 @@ void rp_spmm_set_kernel(rp_spmm_p rp_spmm, const char *name);
 
 /* Device time (seconds since the last clear_stat) spent staging a host B in / a host C out. */
 void rp_spmm_device_times(rp_spmm_p rp_spmm, double *t_h2d, double *t_d2h);
+
+/* Shape of the local-SpMM plan (crp_cuda_spmm_plan_info of include/crp_cuda.h) of this engine. */
+void rp_spmm_plan_info(rp_spmm_p rp_spmm, long long out[12]);
+
+/* Fold the CUDA-event times of every exec issued so far into the engine's public counters (t_pack, t_a2a, t_spmm,
+ * t_exec); synchronises with the device.  After crp_set_blocking(0) the counters lag behind n_exec until this
+ * (or print_stat / clear_stat) is called. */
+void rp_spmm_sync_stats(rp_spmm_p rp_spmm);
+
+/* Host B / C buffers are cudaHostRegister'ed only with CRP_SPMM_PIN_HOST=1 (they must then outlive the engine);
+ * this drops every registration made so far (also done by rp_spmm_free). */
+void crp_unpin_host_all(void);
 
 /* 1 if the engine was created in plan-only mode (CRP_SPMM_PLAN_ONLY=1, no device state). */
 int rp_spmm_is_plan_only(rp_spmm_p rp_spmm);

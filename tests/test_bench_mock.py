@@ -59,7 +59,14 @@ class FakeLib:
         self._host.pop(p.value if hasattr(p, "value") else p, None)
 
 
-for _name in ("crp_set_stream", "crp_set_blocking", "crp_cuda_memset_async", "crp_cuda_event_record", "crp_cuda_stream_sync", "crp_cuda_device_sync",
+    def crp_cuda_measure_dfma_tflops(self):
+        return 37.0
+
+    def rp_spmm_plan_info(self, rp, out):
+        pass
+
+
+for _name in ("rp_spmm_sync_stats", "crp_set_stream", "crp_set_blocking", "crp_cuda_memset_async", "crp_cuda_event_record", "crp_cuda_stream_sync", "crp_cuda_device_sync",
               "crp_cuda_event_sync", "rp_spmm_set_kernel"):
     setattr(FakeLib, _name, lambda self, *a: None)
 
@@ -118,6 +125,11 @@ def test_bench_line_contract(monkeypatch, tmp_path):
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "reference"
     assert d["gpu_launches"] > 0 and abs(d["ms_per_step"] - 0.5) < 1e-9
+    # both arms describe the workload with the same config keys (the driver compares them)
+    assert sorted(d["config"]) == ["driver", "n", "workload"]
+    assert set(("rel_err_max_over_ranks", "rows_checked", "tol", "ok")) <= set(d["parity"])
+    assert "fp64" in d["roofline"] and d["roofline"]["fp64"]["peak_tflops"] == 37.0
+    assert len(d["per_rank"]["rows"]) == 1 and len(d["per_rank"]["rows"][0]) == len(d["per_rank"]["columns"])
 
 
 def test_reference_arm_line(monkeypatch, tmp_path):
@@ -140,3 +152,4 @@ def test_reference_arm_line(monkeypatch, tmp_path):
     assert d["impl"] == "reference" and d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 3
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
+    assert sorted(d["config"]) == ["driver", "n", "workload"]

@@ -107,7 +107,7 @@ def test_kernel_fp32_vs_oracle(mats, name, n):
     assert rel_err(Cd, Cref) <= TOL32, kern
 
 
-@pytest.mark.parametrize("variant", [b"rowsplit", b"rowgroup", b"mergepath"])
+@pytest.mark.parametrize("variant", [b"rowsplit", b"rowgroup", b"panel", b"mergepath"])
 @pytest.mark.parametrize("name", ["rand", "pwtk", "rmat"])
 def test_kernel_variants(mats, name, variant):
     m, k, rp, ci, v = mats[name]
@@ -115,6 +115,10 @@ def test_kernel_variants(mats, name, variant):
     Cref = oracle_spmm(m, 64, rp, ci, v, B)
     Cd, kern = device_spmm(m, k, rp, ci, v, B, variant=variant)
     assert rel_err(Cd, Cref) <= TOL64, kern
+    # a forced variant must really be the kernel that ran (row-group forms exist only for the block-structured matrix)
+    want = {b"rowsplit": "rowsplit", b"mergepath": "mergepath", b"rowgroup": "rowgroup" if name == "pwtk" else "rowsplit",
+            b"panel": "panel" if name == "pwtk" else "rowsplit"}[variant]
+    assert want in kern, (variant, kern)
 
 
 @pytest.mark.parametrize("name", ["rand", "longrows", "pwtk"])
@@ -133,7 +137,7 @@ def test_rowgroup_kernel_is_selected_for_block_structured_rows(mats, name):
     m, k, rp, ci, v = mats[name]
     B = np.random.default_rng(3).uniform(-1, 1, (k, 256))
     Cd, kern = device_spmm(m, k, rp, ci, v, B)
-    assert "rowgroup_f64_R6" in kern, kern
+    assert "panel_f64_R6" in kern, kern          # the B-row-panel form of the row groups (n >= 64, 16-byte aligned operands)
     assert rel_err(Cd, oracle_spmm(m, 256, rp, ci, v, B)) <= TOL64
 
 
