@@ -284,7 +284,8 @@ def main():
     # rp_spmm_sync_stats folds the events of EVERY exec (the counters lag behind n_exec in non-blocking mode)
     L.rp_spmm_sync_stats(pb.rp)
     r = pb.rp.contents
-    nx = max(int(r.n_exec), 1)                 # == a.steps: every timed exec is counted and folded
+    n_exec_counted = int(r.n_exec)
+    nx = max(n_exec_counted, 1)                # == a.steps: every timed exec is counted and folded
     t_spmm = r.t_spmm / nx
     t_pack, t_a2a = r.t_pack / nx, r.t_a2a / nx
     bytes_loc, flops_loc = pb.algorithmic_bytes()
@@ -384,7 +385,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": ach if nproc == 1 else ach_job, "peak": peak, "unit": "GB/s",
                          "frac": (ach if nproc == 1 else ach_job) / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kern,
                          "algorithmic_bytes_per_launch": bytes_loc if nproc == 1 else bytes_sum / nproc, "kernel_ms": kernel_ms,
-                         "kernel_ms_source": "CUDA events around the local-SpMM launches, folded over %d of %d timed execs (rp_spmm_sync_stats)" % (int(r.n_exec), a.steps),
+                         "kernel_ms_source": "CUDA events around the local-SpMM launches, folded over %d of %d timed execs (rp_spmm_sync_stats)" % (n_exec_counted, a.steps),
                          "kernel_share_of_step": kernel_ms / ms_per_step if ms_per_step > 0 else None,
                          "fp64": None if dfma_peak is None else {"achieved_tflops": kernel_tflops, "peak_tflops": dfma_peak, "frac": kernel_tflops / dfma_peak,
                                                                  "peak_source": "measured in this run: 8 independent DFMA chains per thread on all SMs"}},

@@ -68,6 +68,17 @@ struct crp_rowgroup
     int       *d_rest;          // nrest: row ids for the row-split kernel
 };
 
+// nnz-balanced chunks of spmm_mergepath.cu (see mergepath_build.hpp)
+struct crp_mergepath
+{
+    int       nchunks, nlong, nseg;
+    void      *d_desc;          // int4 per chunk
+    int       *d_long_row;      // nlong
+    int       *d_long_sptr;     // nlong + 1
+    void      *d_scratch;       // nseg partial rows
+    size_t    scratch_bytes;
+};
+
 // B-row-panel form of the row groups (spmm_panel.cu / panel_build.hpp): tiles of K groups whose B rows are staged
 // once per thread block in shared memory by cp.async.bulk
 struct crp_rowgroup_host;
@@ -114,6 +125,9 @@ struct crp_spmm_plan
     // nnz-balanced handling of very long rows (power-law matrices), see spmm_longrow.cu
     crp_longrows lr;
     crp_rowgroup rg;
+    crp_mergepath mp;
+    int       mp_tried;         // the merge-path partition has been built (lazily, on the first launch that wants it)
+    int       *h_rowptr;        // host copy of the row pointers (m + 1) for lazily built auxiliary structures
     crp_rowgroup_host *rg_host; // host copy of the row-group arrays (panel construction)
     crp_panel pn;
     char      kernel_name[64];
@@ -121,6 +135,8 @@ struct crp_spmm_plan
 
 void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val, std::vector<int> *rest_out);
 void crp_rowgroup_destroy(crp_spmm_plan *plan);
+void crp_mergepath_build(crp_spmm_plan *plan, const int *rowptr);
+void crp_mergepath_destroy(crp_spmm_plan *plan);
 void crp_panel_build(crp_spmm_plan *plan);
 void crp_panel_destroy(crp_spmm_plan *plan);
 // recv_off[j] .. recv_off[j + 1]: rows of the receive buffer that come from the rank of wait slot j (nslot <= 32)

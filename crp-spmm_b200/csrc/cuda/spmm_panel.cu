@@ -69,15 +69,24 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
     return v;
 }
 
+__device__ __forceinline__ unsigned lds_u32(const unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 template <typename T, int VEC> struct pvec;
 template <> struct pvec<double, 2>
 {
+    static __device__ __forceinline__ void lds_s(const unsigned addr, double (&v)[2]) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr)); }
     static __device__ __forceinline__ void lds(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
     static __device__ __forceinline__ void ldc(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
     static __device__ __forceinline__ void st(double *p, const double (&v)[2]) { __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1])); }
 };
 template <> struct pvec<float, 4>
 {
+    static __device__ __forceinline__ void lds_s(const unsigned addr, float (&v)[4]) { asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr)); }
     static __device__ __forceinline__ void lds(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     static __device__ __forceinline__ void ldc(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     static __device__ __forceinline__ void st(float *p, const float (&v)[4]) { __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3])); }
@@ -109,6 +118,38 @@ __device__ __forceinline__ void lds_vals(const T *p, T (&a)[R])
     }
 }
 
+// the R values of one entry at a 32-bit shared address
+template <typename T, int R>
+__device__ __forceinline__ void lds_vals_s(const unsigned addr, T (&a)[R])
+{
+    constexpr int BYTES = R * (int) sizeof(T);
+    if constexpr (BYTES % 16 == 0)
+    {
+        #pragma unroll
+        for (int i = 0; i < BYTES / 16; i++)
+        {
+            uint4 t;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr + 16u * i));
+            memcpy(reinterpret_cast<char *>(a) + 16 * i, &t, 16);
+        }
+    } else if constexpr (BYTES % 8 == 0) {
+        #pragma unroll
+        for (int i = 0; i < BYTES / 8; i++)
+        {
+            uint2 t;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "r"(addr + 8u * i));
+            memcpy(reinterpret_cast<char *>(a) + 8 * i, &t, 8);
+        }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < BYTES / 4; i++)
+        {
+            unsigned t = lds_u32(addr + 4u * i);
+            memcpy(reinterpret_cast<char *>(a) + 4 * i, &t, 4);
+        }
+    }
+}
+
 }   // namespace
 
 enum { CRP_PANEL_MAXSTAGE = 8, CRP_PANEL_BAR_BYTES = 128 };
@@ -134,13 +175,16 @@ struct panel_args
     const unsigned *flags;              // arrival flags (one 32-bit word per rank)
     const int *wait_idx;                // wait slot -> flag index
     int nwait;
+    int wait_all_first;                 // no wait map for this neighbour list: wait for everybody before the first chunk
     unsigned epoch;
     long long timeout_ns;
     int *err;
 };
 
-template <typename T, int VEC, int R, int U, int K>
-__global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kernel(const panel_args<T> a)
+// FAST: every column slice is full (n is a multiple of the slice width) and all groups are exact - no bounds predicates,
+// no mask tests in the inner loop.  The other instantiation handles partial slices and masked (relaxed-group) entries.
+template <typename T, int VEC, int R, int U, int K, bool FAST>
+__global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel_args<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int W = 32 * U * VEC;                         // dense columns per block
@@ -173,23 +217,59 @@ __global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kerne
         unsigned seen = 0;                                  // wait slots whose flag has been observed
         int s = 0;
         unsigned ph = 1;                                    // parity the empty barrier of stage s is waited on
-        int t = blockIdx.x;
-        int c = -1, cend = -1;
-        if (t < a.ntiles) { c = __ldg(a.tile_chunk_ptr + t); cend = __ldg(a.tile_chunk_ptr + t + 1); }
-        for (;;)
-        {
-            const int cc = (c >= 0) ? c : a.nchunks;        // the stop record closes the stream
-            const int4 dv = __ldg(reinterpret_cast<const int4 *>(a.chunks) + cc);
-            const int uo0 = dv.x, nrows = dv.y;
-            const unsigned mo16 = (unsigned) dv.z, mbytes = (unsigned) dv.w * 16u;
-            int mycol = (lane < nrows) ? __ldg(a.ucol + uo0 + lane) : 0;
-            if (a.chunk_need != NULL && c >= 0)
+
+        // The chunk stream of this block: the chunks of tiles blockIdx.x, blockIdx.x + gridDim.x, ... in order, then the stop
+        // record.  Descriptors are fetched TWO chunks ahead and the panel's column ids ONE chunk ahead of the chunk being
+        // issued, so that the dependent global loads (tile range -> descriptor -> column ids -> row address) are off the
+        // critical path: while the producer sleeps on an empty barrier they complete.  (Round-2 ncu of the first version, which
+        // loaded them in the iteration that used them: consumers spent 29 % of their samples waiting for the full barrier.)
+        int it_t = blockIdx.x, it_c = -1, it_cend = -1, nx_c = -1, nx_cend = -1;
+        if (it_t < a.ntiles) { it_c = __ldg(a.tile_chunk_ptr + it_t); it_cend = __ldg(a.tile_chunk_ptr + it_t + 1); }
+        if (it_t + (int) gridDim.x < a.ntiles) { nx_c = __ldg(a.tile_chunk_ptr + it_t + gridDim.x); nx_cend = __ldg(a.tile_chunk_ptr + it_t + gridDim.x + 1); }
+        bool stop_given = false;
+        auto next_chunk = [&]() -> int {                    // next chunk id of the stream; a.nchunks = stop record; -1 = past the end
+            if (it_c < 0)
             {
-                unsigned need = __ldg(a.chunk_need + cc) & ~seen;
+                if (stop_given) return -1;
+                stop_given = true;
+                return a.nchunks;
+            }
+            const int id = it_c;
+            if (++it_c >= it_cend)
+            {
+                it_t += gridDim.x;
+                if (it_t < a.ntiles)
+                {
+                    it_c = nx_c;  it_cend = nx_cend;
+                    if (it_t + (int) gridDim.x < a.ntiles) { nx_c = __ldg(a.tile_chunk_ptr + it_t + gridDim.x); nx_cend = __ldg(a.tile_chunk_ptr + it_t + gridDim.x + 1); }
+                } else it_c = -1;
+            }
+            return id;
+        };
+        const int4 *descs = reinterpret_cast<const int4 *>(a.chunks);
+        int id0 = next_chunk(), id1 = next_chunk(), id2 = next_chunk();
+        int4 d0 = __ldg(descs + id0);
+        int4 d1 = (id1 >= 0) ? __ldg(descs + id1) : make_int4(0, 0, 0, 0);
+        int col0 = (lane < d0.y) ? __ldg(a.ucol + d0.x + lane) : 0;
+        while (id0 >= 0)
+        {
+            const int4 d2 = (id2 >= 0) ? __ldg(descs + id2) : make_int4(0, 0, 0, 0);
+            const int col1 = (id1 >= 0 && lane < d1.y) ? __ldg(a.ucol + d1.x + lane) : 0;
+            const int uo0 = d0.x, nrows = d0.y;
+            const unsigned mo16 = (unsigned) d0.z, mbytes = (unsigned) d0.w * 16u;
+            const bool is_stop = (id0 == a.nchunks);
+            if (a.nwait > 0)
+            {
+                // chunks that read received rows wait for the ranks that send them; the stop record waits for every neighbour
+                // (a rank that has seen all flags of epoch e knows that nobody reads the buffer half epoch e + 1 overwrites)
+                unsigned need = 0;
+                if (is_stop || a.wait_all_first) need = (a.nwait >= 32) ? 0xffffffffu : ((1u << a.nwait) - 1u);
+                else if (a.chunk_need != NULL) need = __ldg(a.chunk_need + id0);
+                need &= ~seen;
                 if (need)
                 {
-                    // one lane per missing neighbour spins on its arrival flag; rows written by the peer's stores
-                    // are ordered before the flag (st.release.sys after __threadfence_system on the sender)
+                    // one lane per missing neighbour spins on its arrival flag; the rows were written by the peer's stores
+                    // before the flag (fence + st.release.sys on the sender)
                     if (lane < a.nwait && ((need >> lane) & 1u))
                     {
                         const unsigned *f = a.flags + a.wait_idx[lane];
@@ -213,6 +293,7 @@ __global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kerne
             __syncwarp();
             if (lane == 0) bulk_g2s(metas + (size_t) s * a.meta_max, a.meta + (size_t) mo16 * 16, mbytes, &full[s]);
             unsigned char *dst = rows + (size_t) s * a.CR * RBW;
+            int mycol = col0;
             for (int r = lane; r < nrows; r += 32)
             {
                 if (r >= 32) mycol = __ldg(a.ucol + uo0 + r);
@@ -220,22 +301,24 @@ __global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kerne
                 bulk_g2s(dst + (size_t) r * RBW, src, rb, &full[s]);
             }
             if (++s == nstage) { s = 0; ph ^= 1u; }
-            if (c < 0) break;
-            if (++c >= cend)
-            {
-                t += gridDim.x;
-                if (t < a.ntiles) { c = __ldg(a.tile_chunk_ptr + t); cend = __ldg(a.tile_chunk_ptr + t + 1); }
-                else c = -1;
-            }
+            id0 = id1;  id1 = id2;  id2 = next_chunk();
+            d0 = d1;  d1 = d2;  col0 = col1;
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumers
+    // Everything a consumer reads in its inner loop is shared memory addressed with 32-bit addresses and immediate offsets:
+    // per entry one LDS (slot word, fetched two entries ahead), U 128-bit LDS of the B row slice, the R values (broadcast),
+    // R * U * VEC FMAs.  The entry lists are padded with two dummy entries (panel_build.hpp), so the software pipeline
+    // never needs a bounds check before it prefetches.
     const int w = warp - 1;
-    int voff[U];                                            // element offset of this lane's column vectors; -1: beyond the slice
+    constexpr int UB = 32 * VEC * (int) sizeof(T);          // bytes between a lane's consecutive column vectors
+    bool valid[U];
     #pragma unroll
-    for (int u = 0; u < U; u++) { const int v = (u * 32 + lane) * VEC; voff[u] = (v < ncols) ? v : -1; }
+    for (int u = 0; u < U; u++) valid[u] = FAST || ((u * 32 + lane) * VEC < ncols);
+    const unsigned rows_s = smem_u32(rows) + (unsigned) lane * VEC * (unsigned) sizeof(T);
+    const unsigned metas_s = smem_u32(metas);
 
     T acc[R][U][VEC];
     int row0 = -1;
@@ -244,38 +327,36 @@ __global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kerne
     for (;; s = (s + 1 == nstage) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u)
     {
         mbar_wait(&full[s], ph);
-        const unsigned char *mrec = metas + (size_t) s * a.meta_max;
-        const int *hdr = reinterpret_cast<const int *>(mrec);
-        const int flags = hdr[1];
+        const unsigned mrec = metas_s + (unsigned) s * a.meta_max;
+        const int flags = (int) lds_u32(mrec + 4);
         if (flags & CRP_PANEL_STOP) break;
-        const int e0 = hdr[2 + K + w], e1 = hdr[3 + K + w], ne = hdr[2 + 2 * K];
+        const int e0 = (int) lds_u32(mrec + 4 * (2 + K + w)), e1 = (int) lds_u32(mrec + 4 * (3 + K + w)), ne = (int) lds_u32(mrec + 4 * (2 + 2 * K));
         if (flags & CRP_PANEL_FIRST)
         {
-            row0 = hdr[2 + w];
+            row0 = (int) lds_u32(mrec + 4 * (2 + w));
             #pragma unroll
             for (int r = 0; r < R; r++)
                 #pragma unroll
                 for (int u = 0; u < U; u++)
                     #pragma unroll
-                    for (int e = 0; e < VEC; e++) acc[r][u][e] = (T) 0;
+                    for (int q = 0; q < VEC; q++) acc[r][u][q] = (T) 0;
         }
-        const unsigned *slots = reinterpret_cast<const unsigned *>(mrec + HDR);
-        const T *vals = reinterpret_cast<const T *>(mrec + HDR + (((size_t) ne * 4 + 15) & ~(size_t) 15));
-        const T *xs = reinterpret_cast<const T *>(rows + (size_t) s * a.CR * RBW);
+        const unsigned slot_a = mrec + HDR;
+        const unsigned val_a = slot_a + ((((unsigned) ne + 2u) * 4u + 15u) & ~15u);
+        const unsigned x_a = rows_s + (unsigned) s * (unsigned) a.CR * RBW;
 
-        auto load = [&](const int e, unsigned &sm, T (&av)[R], T (&xv)[U][VEC]) {
-            sm = slots[e];
-            lds_vals<T, R>(vals + (size_t) e * R, av);
-            const T *xr = xs + (size_t) (sm & 0xffffu) * W;
+        auto ldx = [&](const unsigned sm, T (&xv)[U][VEC]) {
+            const unsigned xr = x_a + (sm & 0xffffu) * RBW;
             #pragma unroll
             for (int u = 0; u < U; u++)
             {
-                if (voff[u] >= 0) pvec<T, VEC>::lds(xr + voff[u], xv[u]);
+                if (FAST || valid[u]) pvec<T, VEC>::lds_s(xr + u * UB, xv[u]);
                 else { for (int q = 0; q < VEC; q++) xv[u][q] = (T) 0; }
             }
         };
-        auto fmas = [&](const unsigned sm, const T (&av)[R], const T (&xv)[U][VEC]) {
-            if ((sm >> 16) == FULLMASK)
+        auto lda = [&](const int e, T (&av)[R]) { lds_vals_s<T, R>(val_a + (unsigned) e * (R * (unsigned) sizeof(T)), av); };
+        auto fm = [&](const unsigned sm, const T (&av)[R], const T (&xv)[U][VEC]) {
+            if (FAST || (sm >> 16) == FULLMASK)
             {
                 #pragma unroll
                 for (int r = 0; r < R; r++)
@@ -297,21 +378,25 @@ __global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kerne
             }
         };
 
-        int e = e0;
-        if (e < e1)
         {
-            unsigned sa, sb;
+            int e = e0;
+            unsigned s0 = lds_u32(slot_a + 4u * (unsigned) e), s1 = lds_u32(slot_a + 4u * (unsigned) e + 4u);
             T aa[R], ab[R], xa[U][VEC], xb[U][VEC];
-            load(e, sa, aa, xa);
-            for (;;)
+            ldx(s0, xa);
+            lda(e, aa);
+            while (e + 2 <= e1)
             {
-                if (e + 1 < e1) load(e + 1, sb, ab, xb);
-                fmas(sa, aa, xa);
-                if (++e >= e1) break;
-                if (e + 1 < e1) load(e + 1, sa, aa, xa);
-                fmas(sb, ab, xb);
-                if (++e >= e1) break;
+                const unsigned s2 = lds_u32(slot_a + 4u * (unsigned) e + 8u);
+                ldx(s1, xb);
+                lda(e + 1, ab);
+                fm(s0, aa, xa);
+                const unsigned s3 = lds_u32(slot_a + 4u * (unsigned) e + 12u);
+                ldx(s2, xa);
+                lda(e + 2, aa);
+                fm(s1, ab, xb);
+                s0 = s2;  s1 = s3;  e += 2;
             }
+            if (e < e1) fm(s0, aa, xa);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);              // this warp is done with stage s
@@ -321,11 +406,11 @@ __global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kerne
             #pragma unroll
             for (int r = 0; r < R; r++)
             {
-                T *crow = a.C + (size_t) (row0 + r) * a.ldc + col0;
+                T *crow = a.C + (size_t) (row0 + r) * a.ldc + col0 + lane * VEC;
                 #pragma unroll
                 for (int u = 0; u < U; u++)
                 {
-                    if (voff[u] < 0) continue;
+                    if (!(FAST || valid[u])) continue;
                     T out[VEC];
                     if (a.beta == (T) 0)
                     {
@@ -333,11 +418,11 @@ __global__ void __maxnreg__(((65536 / ((K + 1) * 32)) / 8) * 8) spmm_panel_kerne
                         for (int q = 0; q < VEC; q++) out[q] = a.alpha * acc[r][u][q];
                     } else {
                         T old[VEC];
-                        pvec<T, VEC>::ldc(crow + voff[u], old);
+                        pvec<T, VEC>::ldc(crow + u * 32 * VEC, old);
                         #pragma unroll
                         for (int q = 0; q < VEC; q++) out[q] = fma(a.alpha, acc[r][u][q], a.beta * old[q]);
                     }
-                    pvec<T, VEC>::st(crow + voff[u], out);
+                    pvec<T, VEC>::st(crow + u * 32 * VEC, out);
                 }
             }
         }
@@ -362,7 +447,7 @@ static void *panel_upload(const void *src, const size_t bytes)
 }
 
 // Build the panel form for the plan's row groups (called once at plan creation; the meta records of a value type
-// are made on the first exec with that type).  Parameters: CRP_PANEL_K (8 or 12 groups per tile), CRP_PANEL_CR rows and
+// are made on the first exec with that type).  Parameters: CRP_PANEL_CR rows and
 // CRP_PANEL_EMAX blocks per chunk; defaults sized so that three to four stages of 2 KB row slices fit into 227 KB.
 void crp_panel_build(crp_spmm_plan *plan)
 {
@@ -371,8 +456,7 @@ void crp_panel_build(crp_spmm_plan *plan)
     const crp_rowgroup_host *rg = plan->rg_host;
     if (rg == NULL || rg->R < 2 || rg->g_row.empty() || plan->n_hint < 64) return;
     if (panel_env_int("CRP_SPMM_PANEL", 1) == 0) return;
-    int K = panel_env_int("CRP_PANEL_K", 8);
-    if (K != 8 && K != 12) K = 8;
+    const int K = 8;        // 8 consumer warps + the producer = 9 warps: two consumers per scheduler (K = 11 measured slower, round 2)
     int CR = panel_env_int("CRP_PANEL_CR", 32);
     if (CR < 4) CR = 4;
     if (CR > 64) CR = 64;
@@ -447,7 +531,7 @@ void crp_panel_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *rec
 
 // ------------------------------------------------------------------------------------- launch
 
-template <typename T, int VEC, int R, int U, int K>
+template <typename T, int VEC, int R, int U, int K, bool FAST>
 static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cudaStream_t s)
 {
     crp_panel *pn = &plan->pn;
@@ -467,7 +551,7 @@ static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cu
     if (nstage < 2) return false;
     args.nstage = nstage;
     const size_t smem = CRP_PANEL_BAR_BYTES + (size_t) nstage * stage;
-    auto kern = spmm_panel_kernel<T, VEC, R, U, K>;
+    auto kern = spmm_panel_kernel<T, VEC, R, U, K, FAST>;
     static bool attr_set = false;
     if (!attr_set) { CRP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); attr_set = true; }
     const int nslice = (args.n + W - 1) / W;
@@ -485,18 +569,13 @@ template <typename T, int VEC, int R>
 static bool panel_launch_R(crp_spmm_plan *plan, const panel_args<T> &args, cudaStream_t s)
 {
     const int nv = args.n / VEC;
-    const int K = plan->pn.K;
     constexpr int UMAX = (R * VEC * (int) sizeof(T) <= 6 * 16) ? 4 : 2;      // accumulator tile <= 96 registers, as in spmm_rowgroup.cu
-#define CRP_PN(U, K_) panel_launch_cfg<T, VEC, R, (U <= UMAX ? U : UMAX), K_>(plan, args, s)
-    if (K == 12)
-    {
-        if (nv >= 128) return CRP_PN(4, 12);
-        if (nv >= 64)  return CRP_PN(2, 12);
-        return CRP_PN(1, 12);
-    }
-    if (nv >= 128) return CRP_PN(4, 8);
-    if (nv >= 64)  return CRP_PN(2, 8);
-    return CRP_PN(1, 8);
+    const int U = (nv >= 128 && UMAX >= 4) ? 4 : (nv >= 64 ? 2 : 1);
+    const bool fast = plan->rg.exact && (args.n % (32 * U * VEC) == 0);
+#define CRP_PN(U_) (fast ? panel_launch_cfg<T, VEC, R, U_, 8, true>(plan, args, s) : panel_launch_cfg<T, VEC, R, U_, 8, false>(plan, args, s))
+    if (U == 4) { if constexpr (UMAX >= 4) return CRP_PN(4); else return false; }
+    if (U == 2) return CRP_PN(2);
+    return CRP_PN(1);
 #undef CRP_PN
 }
 
@@ -529,9 +608,11 @@ bool crp_launch_panel(
     a.n = n;
     a.alpha = alpha;  a.beta = beta;
     a.C = C;  a.ldc = ldc;
-    if (wait != NULL && wait->nwait > 0 && pn->d_chunk_need != NULL)
+    if (wait != NULL && wait->nwait > 0)
     {
-        a.chunk_need = pn->d_chunk_need;
+        if (wait->nwait > 32) return false;                 // the caller waits with the separate kernel
+        a.chunk_need = (pn->nslot == wait->nwait) ? pn->d_chunk_need : NULL;
+        a.wait_all_first = (pn->nslot == wait->nwait) ? 0 : 1;
         a.flags = wait->flags;  a.wait_idx = wait->wait_idx;  a.nwait = wait->nwait;
         a.epoch = wait->epoch;  a.timeout_ns = wait->timeout_ns;  a.err = wait->err;
     }

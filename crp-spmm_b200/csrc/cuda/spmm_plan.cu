@@ -14,6 +14,10 @@ void crp_launch_rowsplit(
 );
 template <typename T>
 void crp_launch_longrow_reduce(const crp_longrows *lr, const int n, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
+template <typename T, int VECN>
+bool crp_launch_mergepath(
+    crp_spmm_plan *plan, const T *val, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s
+);
 template <typename T, int VEC>
 bool crp_launch_panel(
     crp_spmm_plan *plan, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc,
@@ -51,6 +55,10 @@ extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, co
     crp_rowgroup_build(p, rowptr_h, colidx_h, val_h, &rest);
     if (p->rg.R > 1) crp_longrows_build(p, rowptr_h, rest.data(), (int) rest.size());
     else crp_longrows_build(p, rowptr_h, NULL, m);
+    // nnz-balanced chunks for matrices without row-group structure (kept on the host side until a launch wants them:
+    // the partition is cheap, O(m)); automatic choice: skewed row lengths, see spmm_dispatch
+    p->h_rowptr = (int *) malloc(sizeof(int) * ((size_t) m + 1));
+    if (m > 0) memcpy(p->h_rowptr, rowptr_h, sizeof(int) * ((size_t) m + 1)); else p->h_rowptr[0] = 0;
     return p;
 }
 
@@ -63,6 +71,8 @@ extern "C" void crp_cuda_spmm_plan_destroy(crp_spmm_plan *plan)
     if (plan->d_val32)  CRP_CUDA_CHECK(cudaFree(plan->d_val32));
     crp_longrows_destroy(plan);
     crp_rowgroup_destroy(plan);
+    crp_mergepath_destroy(plan);
+    free(plan->h_rowptr);
     free(plan);
 }
 
@@ -130,18 +140,30 @@ static void spmm_dispatch(
     const bool want_pn = (plan->variant == CRP_VARIANT_AUTO || plan->variant == CRP_VARIANT_PANEL);
     if (want_pn && rg->R > 1 && rg->ngroups > 0)
     {
-        // the rest rows go first when the panel kernel does the waiting: they may need received rows too
-        if (rg->nrest > 0) wait_first(wait, s);
-        if (crp_launch_panel<T, VECN>(plan, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, rg->nrest > 0 ? NULL : wait, s))
+        // the panel kernel waits for the neighbours itself (and for all of them before it ends), so the rest rows,
+        // which may read received rows too, follow it on the stream
+        if (crp_launch_panel<T, VECN>(plan, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, wait, s))
         {
             if (rg->nrest > 0) rowsplit_balanced<T, VECN>(plan, true, rg->nrest, rg->d_rest, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s);
             snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_panel_%s_R%d_K%d%s%s", tname, rg->R, plan->pn.K, rg->nrest > 0 ? "+rowsplit" : "", rg->nrest > 0 ? lr_tag : "");
             plan->last_kernel = plan->kernel_name;
             return;
         }
-        if (rg->nrest > 0) wait = NULL;          // already waited
     }
     wait_first(wait, s);
+    // nnz-balanced kernel: forced, or chosen for matrices without row groups whose longest row is far above the average
+    // (power-law graphs: one-row-per-warp leaves most warps idle behind the hubs)
+    const bool skewed = (rg->R <= 1) && plan->avg_row_nnz > 0.0 && (double) plan->max_row_nnz > 16.0 * plan->avg_row_nnz + 64.0;
+    if (plan->variant == CRP_VARIANT_MERGEPATH || (plan->variant == CRP_VARIANT_AUTO && skewed))
+    {
+        if (plan->mp.nchunks == 0 && !plan->mp_tried) { crp_mergepath_build(plan, plan->h_rowptr); plan->mp_tried = 1; }
+        if (crp_launch_mergepath<T, VECN>(plan, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s))
+        {
+            snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_mergepath_%s%s", tname, plan->mp.nlong > 0 ? "+fixup" : "");
+            plan->last_kernel = plan->kernel_name;
+            return;
+        }
+    }
     if (want_rg && rg->R > 1 && rg->ngroups > 0 && rg->exact)
     {
         const uintptr_t ptrs = (uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C;
@@ -197,7 +219,7 @@ extern "C" void crp_cuda_spmm_exec_wait(
                                  alpha, beta, (double *) C, (size_t) ldc, wait, s, "f64");
     } else if (elem_size == 4) {
         cast_to_f32(plan->d_val, &plan->d_val32, (size_t) plan->nnz, s);
-        cast_to_f32(plan->rg.d_bval, &plan->rg.d_bval32, (size_t) plan->rg.nblk * (size_t) plan->rg.R, s);
+        if (plan->rg.d_bval != NULL) cast_to_f32(plan->rg.d_bval, &plan->rg.d_bval32, (size_t) plan->rg.nblk * (size_t) plan->rg.R, s);
         spmm_dispatch<float, 4>(plan, plan->d_val32, plan->rg.d_bval32, n, (const float *) X0, (size_t) ldx0, (const float *) X1, (size_t) ldx1,
                                 (float) alpha, (float) beta, (float *) C, (size_t) ldc, wait, s, "f32");
     } else {
@@ -214,7 +236,7 @@ extern "C" void crp_cuda_spmm_plan_info(const crp_spmm_plan *plan, long long out
     out[1] = plan->rg.ngroups;  out[2] = plan->rg.nblk;  out[3] = plan->rg.R > 1 ? plan->rg.nrest : plan->m;
     out[4] = plan->rg.R > 1 ? plan->rg.rest_nnz : plan->nnz;
     out[5] = plan->pn.ntiles;  out[6] = plan->pn.nchunks;  out[7] = plan->pn.union_rows;
-    out[8] = plan->rg.exact;  out[9] = plan->lr.nlong;  out[10] = plan->nnz;  out[11] = 0;
+    out[8] = plan->rg.exact;  out[9] = plan->lr.nlong;  out[10] = plan->nnz;  out[11] = plan->mp.nchunks;
 }
 
 extern "C" const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan) { return plan ? plan->last_kernel : "none"; }

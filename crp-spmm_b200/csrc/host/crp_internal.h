@@ -89,7 +89,9 @@ struct crp_rp_dev
     int     dst_elem_size;      /* element size the tables were built for                                   */
     void    *d_flag_ptrs;  int n_flag;      /* addresses of this rank's arrival flag on the peers it sends to */
     int     *d_wait_idx;   int n_wait;      /* ranks whose arrival flag this rank waits for                   */
-    int     *h_err;             /* pinned: set by the wait kernel on timeout                                */
+    int     *h_err;             /* pinned: set by the wait kernel / the SpMM kernel on timeout              */
+    unsigned int *d_put_counter; /* device word: blocks of the put kernel that have finished (reset by the kernel) */
+    int     p2p_hostsync;       /* ranks share a GPU: arrival is established by a host barrier, kernels never spin on each other */
     unsigned int epoch;
     crp_nccl_comm *nc;          /* NCCL communicator used for the B-row exchange                     */
     int     *peer_nc_rank;      /* nproc: rank of each member of rp->comm inside nc                  */

@@ -255,9 +255,22 @@ static int rp_p2p_setup(rp_spmm_p rp, struct crp_rp_dev *d)
     if (d->n_flag) { crp_cuda_malloc_dev(&d->d_flag_ptrs, sizeof(void *) * (size_t) d->n_flag); crp_cuda_memcpy_h2d(fp, d->d_flag_ptrs, sizeof(void *) * (size_t) d->n_flag); }
     if (d->n_wait) { crp_cuda_malloc_dev((void **) &d->d_wait_idx, sizeof(int) * (size_t) d->n_wait); crp_cuda_memcpy_h2d(wi, d->d_wait_idx, sizeof(int) * (size_t) d->n_wait); }
     free(fp);
-    free(wi);
+    int *wi_copy = wi;
     crp_cuda_malloc_host((void **) &d->h_err, sizeof(int));
     *d->h_err = 0;
+    crp_cuda_malloc_dev((void **) &d->d_put_counter, sizeof(unsigned int));
+    crp_cuda_memset_dev(d->d_put_counter, 0, sizeof(unsigned int));
+    /* wait map of the local-SpMM plans: which neighbour's flag a piece of work depends on (rows of the receive buffer are
+     * grouped by sending rank, ranks ascending - the order of the wait slots) */
+    {
+        int *roff = (int *) xmalloc(sizeof(int) * ((size_t) d->n_wait + 1));
+        for (int j = 0; j < d->n_wait; j++) roff[j] = d->recv_rows[wi_copy[j]];
+        roff[d->n_wait] = d->n_recv_rows;
+        crp_cuda_spmm_set_wait_map(d->plan, d->n_wait, roff);
+        if (d->plan_off) crp_cuda_spmm_set_wait_map(d->plan_off, d->n_wait, roff);
+        free(roff);
+    }
+    free(wi_copy);
     d->epoch = 0;
     d->dst_elem_size = 0;
     MPI_Barrier(rp->comm);
@@ -293,6 +306,7 @@ static void rp_p2p_teardown(rp_spmm_p rp, struct crp_rp_dev *d)
     crp_cuda_free_dev(d->d_dst_rows[1]);
     crp_cuda_free_dev(d->d_flag_ptrs);
     crp_cuda_free_dev(d->d_wait_idx);
+    crp_cuda_free_dev(d->d_put_counter);
     crp_cuda_free_host(d->h_err);
     free(d->peer_mem); free(d->peer_half_bytes); free(d->peer_recv_off);
 }
@@ -349,10 +363,17 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     MPI_Comm_size(MPI_COMM_WORLD, &wsize);
     int transport;
     GET_ENV_INT_VAR(transport, "CRP_SPMM_TRANSPORT", "transport", -1, 0, 2, 0);   /* 0 NCCL, 1 staged MPI, 2 NVLink peer stores */
-    if (wsize > crp_cuda_device_count()) transport = 1;
+    /* Ranks that share a GPU (more ranks than devices; NCCL cannot do that): the default is the host-staged transport.
+     * CRP_SPMM_TRANSPORT=2 is honoured there too - CUDA IPC maps a peer's buffer on the same device just as well - but
+     * kernels of different processes on ONE GPU must never spin on each other (nothing guarantees that they run at the
+     * same time), so the arrival of the rows is established by a host barrier after the put kernels have completed
+     * ("hostsync"); the flags are still written, and read (already satisfied) by the SpMM kernel. */
+    const int shared_gpu = (wsize > crp_cuda_device_count());
+    if (shared_gpu && transport != 2) transport = 1;
     else if (transport < 0) transport = CRP_DEFAULT_TRANSPORT;
     d->staged = (transport == 1);
     d->p2p = (transport == 2 && nproc > 1);
+    d->p2p_hostsync = (d->p2p && shared_gpu) ? 1 : 0;
 
     /* Overlap mode (default with NCCL): the product is split by column into the part that needs only
      * this rank's own B rows - it runs while the exchange is in flight - and the part that needs
@@ -362,8 +383,13 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
      * costs more than it hides (0.213 vs 0.204 ms per exec), so the threshold is a few MB. */
     int want_overlap;
     GET_ENV_INT_VAR(want_overlap, "CRP_SPMM_OVERLAP", "overlap", -1, 0, 1, 0);
-    if (want_overlap < 0) want_overlap = ((size_t) d->n_recv_rows * (size_t) n * sizeof(double) >= ((size_t) 4 << 20)) ? 1 : 0;
-    d->overlap = (want_overlap && nproc > 1 && !d->staged && (d->n_send_rows > 0 || d->n_recv_rows > 0)) ? 1 : 0;
+    const int auto_overlap = ((size_t) d->n_recv_rows * (size_t) n * sizeof(double) >= ((size_t) 4 << 20)) ? 1 : 0;
+    /* the peer-memory transport overlaps inside the SpMM kernel (it waits for a neighbour right before the first piece of
+     * work that reads its rows), so the split is only made there when asked for explicitly */
+    if (want_overlap < 0 && transport == 2) want_overlap = 0;
+    if (want_overlap < 0 && d->staged) want_overlap = 0;
+    if (want_overlap < 0) want_overlap = auto_overlap;
+    d->overlap = (want_overlap && nproc > 1 && (d->n_send_rows > 0 || d->n_recv_rows > 0)) ? 1 : 0;
     if (d->overlap && d->n_recv_rows > 0)
     {
         const int m = rp->A_nrow;
@@ -404,6 +430,8 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     d->nc = NULL;
     d->peer_nc_rank = NULL;
     if (d->p2p) d->p2p = rp_p2p_setup(rp, d);
+    if (!d->p2p) d->p2p_hostsync = 0;
+    if (!d->p2p && shared_gpu) d->staged = 1;
     if (nproc > 1 && !d->staged && !d->p2p)
     {
         d->nc = crp_nccl_get(nccl_parent);
@@ -658,18 +686,33 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         crp_cuda_stream_wait_event(cs, mark[CRP_EV_B_IN]);
     }
     const void *X1 = d->d_recvbuf;
+    /* peer-memory transport without the overlap split: the SpMM kernel itself waits for the neighbours' flags */
+    int kwait = 0;
     if (d->p2p && n > 0)
     {
-        /* gather + NVLink stores into the peers' receive halves, arrival flags, wait for the neighbours' flags */
+        /* one launch: gather + NVLink stores into the peers' receive halves, then this rank's arrival flag on every neighbour */
         rp_p2p_tables(rp, d, elem_size);
         d->epoch++;
         const int half = (int) (d->epoch & 1u);
-        if (d->n_send_rows > 0) crp_cuda_put_rows(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, (void *const *) d->d_dst_rows[half], cs);
-        CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0, cs);
-        crp_cuda_signal_peers((unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, cs);
-        crp_cuda_wait_flags((const unsigned int *) d->p2p_mem, d->d_wait_idx, d->n_wait, d->epoch, CRP_P2P_TIMEOUT_S, d->h_err, cs);
-        CRP_MARK_ON(CRP_EV_XCHG, overlap || d->n_flag > 0, cs);
+        crp_cuda_put_rows_signal(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, (void *const *) d->d_dst_rows[half],
+                                 (unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, d->d_put_counter, cs);
+        CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0 || d->n_flag > 0, cs);
         X1 = (const char *) d->p2p_mem + CRP_P2P_HDR + (size_t) half * d->p2p_half_bytes;
+        if (d->p2p_hostsync)
+        {
+            /* ranks sharing one GPU: no kernel may spin on another process' kernel - a host barrier after the puts have
+             * completed establishes the arrival; the flags are then already set when the SpMM kernel reads them */
+            crp_cuda_stream_sync(cs);
+            MPI_Barrier(rp->comm);
+        }
+        if (overlap)
+        {
+            crp_cuda_wait_flags((const unsigned int *) d->p2p_mem, d->d_wait_idx, d->n_wait, d->epoch, CRP_P2P_TIMEOUT_S, d->h_err, cs);
+            CRP_MARK_ON(CRP_EV_XCHG, 1, cs);
+        } else {
+            kwait = d->n_wait;
+            mark[CRP_EV_XCHG] = mark[CRP_EV_PACKED];
+        }
     } else {
         if (d->n_send_rows > 0 && n > 0)
         {
@@ -696,8 +739,10 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     if (!overlap)
     {
         mark[CRP_EV_DIAG] = mark[CRP_EV_OFF0] = mark[CRP_EV_XCHG];
-        if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd, stream);
-        CRP_MARK(CRP_EV_SPMM, m > 0 && n > 0);
+        if (n > 0 && (m > 0 || kwait > 0))
+            crp_cuda_spmm_exec_wait(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd,
+                                    (const unsigned int *) d->p2p_mem, d->d_wait_idx, kwait, d->epoch, CRP_P2P_TIMEOUT_S, d->h_err, stream);
+        CRP_MARK(CRP_EV_SPMM, n > 0 && (m > 0 || kwait > 0));
     } else {
         if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd, stream);
         CRP_MARK(CRP_EV_DIAG, 1);
@@ -757,6 +802,16 @@ const char *rp_spmm_kernel_name(rp_spmm_p rp)
 {
     if (rp == NULL || rp->dev == NULL) return "none";
     return crp_cuda_spmm_last_kernel(((struct crp_rp_dev *) rp->dev)->plan);
+}
+
+const char *rp_spmm_transport_name(rp_spmm_p rp)
+{
+    if (rp == NULL || rp->dev == NULL) return "none";
+    const struct crp_rp_dev *d = (const struct crp_rp_dev *) rp->dev;
+    if (rp->nproc == 1) return "single";
+    if (d->p2p) return d->p2p_hostsync ? (d->overlap ? "p2p-hostsync+overlap" : "p2p-hostsync") : (d->overlap ? "p2p+overlap" : "p2p");
+    if (d->staged) return d->overlap ? "staged+overlap" : "staged";
+    return d->overlap ? "nccl+overlap" : "nccl";
 }
 
 void rp_spmm_set_kernel(rp_spmm_p rp, const char *name)

@@ -147,6 +147,8 @@ def load():
     L.rp_spmm_kernel_name.argtypes = [C.POINTER(RowparaSpmm)]
     L.rp_spmm_kernel_name.restype = C.c_char_p
     L.rp_spmm_set_kernel.argtypes = [C.POINTER(RowparaSpmm), C.c_char_p]
+    L.rp_spmm_transport_name.argtypes = [C.POINTER(RowparaSpmm)]
+    L.rp_spmm_transport_name.restype = C.c_char_p
     L.rp_spmm_device_times.argtypes = [C.POINTER(RowparaSpmm), c_double_p, c_double_p]
     L.para2d_spmm_init.argtypes = [i, i, i, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.POINTER(Para2dSpmm))]
     L.para2d_spmm_free.argtypes = [C.POINTER(C.POINTER(Para2dSpmm))]

@@ -209,6 +209,7 @@ def main(argv=None):
                 pb.exec_host(B, C_)
         out["C"] = pb.C_rowmajor(C_)
         out["kernel"] = np.array(pb.L.rp_spmm_kernel_name(pb.rp).decode())
+        out["transport"] = np.array(pb.L.rp_spmm_transport_name(pb.rp).decode())
         if a.stat:
             pb.print_stat()
     if a.dump:

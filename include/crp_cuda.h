@@ -102,6 +102,12 @@ void *crp_cuda_ipc_open(const void *handle64);                  /* NULL on failu
 void  crp_cuda_ipc_close(void *peer_ptr);
 /* dst_rows_d[i] (a device array of peer addresses) := src[ridx_d[i], 0:ncol]; one launch for all peers */
 void  crp_cuda_put_rows(size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, const int *ridx_d, void *const *dst_rows_d, void *stream);
+/* crp_cuda_put_rows followed by crp_cuda_signal_peers in ONE launch (the last thread block to finish publishes the flags);
+ * done_counter_d: one zero-initialised device word owned by the caller, reset by the kernel.  nrow == 0: only signals. */
+void  crp_cuda_put_rows_signal(
+    size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, const int *ridx_d, void *const *dst_rows_d,
+    unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, unsigned int *done_counter_d, void *stream
+);
 /* after the puts (same stream): *flag_ptrs_d[j] := epoch for j < nflag, with system-scope release */
 void  crp_cuda_signal_peers(unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, void *stream);
 /* spin until every flags_d[wait_idx_d[j]] has reached epoch, j < nwait; on timeout (seconds) *err_d is set to 1 and the kernel returns */

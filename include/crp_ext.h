@@ -35,7 +35,11 @@ int crp_nccl_version(void);
 
 /* Name of the local-SpMM kernel variant the engine's last exec launched. */
 const char *rp_spmm_kernel_name(rp_spmm_p rp_spmm);
-/* Force a variant ("auto", "rowsplit", "rowgroup", "mergepath") for experiments. */
+/* Data plane of the B-row exchange this engine uses: "single" (one rank), "p2p" (NVLink peer stores + arrival flags, the
+ * SpMM kernel waits itself), "p2p-hostsync" (same stores between ranks that share a GPU, arrival by host barrier), "nccl",
+ * "staged" (pinned host memory + MPI); "+overlap" when the product is split into own-rows / received-rows passes. */
+const char *rp_spmm_transport_name(rp_spmm_p rp_spmm);
+/* Force a variant ("auto", "rowsplit", "rowgroup", "panel", "mergepath") for experiments. */
 void rp_spmm_set_kernel(rp_spmm_p rp_spmm, const char *name);
 
 /* Device time (seconds since the last clear_stat) spent staging a host B in / a host C out. */

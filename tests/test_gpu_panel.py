@@ -51,8 +51,8 @@ def test_panel_fp32(pw, n):
     assert rel_err(Cd, oracle_spmm(m, n, rp, ci, v.astype(np.float32).astype(np.float64), B.astype(np.float64))) <= TOL32
 
 
-@pytest.mark.parametrize("cfg", [dict(CRP_PANEL_K="12"), dict(CRP_PANEL_CR="4", CRP_PANEL_EMAX="8"), dict(CRP_PANEL_CR="16", CRP_PANEL_STAGES="2"),
-                                 dict(CRP_PANEL_CR="64"), dict(CRP_PANEL_GRID="3")])
+@pytest.mark.parametrize("cfg", [dict(CRP_PANEL_CR="4", CRP_PANEL_EMAX="8"), dict(CRP_PANEL_CR="16", CRP_PANEL_STAGES="2"),
+                                 dict(CRP_PANEL_CR="48"), dict(CRP_PANEL_GRID="3")])
 def test_panel_configurations(pw, cfg):
     """tile width, chunk size, pipeline depth and grid size change the schedule, never the result (bit for bit)"""
     m, k, rp, ci, v = pw

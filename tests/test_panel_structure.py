@@ -54,7 +54,7 @@ def perturb(mat, frac, seed=5):
     return m, k, nrp.astype(np.int32), ci[keep], v[keep]
 
 
-@pytest.mark.parametrize("K,CR,EMAX", [(8, 32, 128), (12, 16, 48), (8, 4, 8), (8, 64, 256)])
+@pytest.mark.parametrize("K,CR,EMAX", [(8, 32, 128), (8, 16, 48), (8, 4, 8), (8, 64, 256)])
 def test_pwtk_like_exact_groups(emul, K, CR, EMAX):
     mat = gen.pwtk_like(m=6000, target_nnz=316000, bandwidth=5000, grid_w=16, seed=11)
     s = run(emul, mat, 8, K, CR, EMAX)
