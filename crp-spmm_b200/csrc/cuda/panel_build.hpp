@@ -17,12 +17,12 @@
 //   int32  grow[K]        first C row of each consumer's group (-1: no such group in this tile)
 //   int32  eoff[K + 1]    entry range of each consumer inside this chunk
 //   (pad to 16 B)
-//   uint32 slot[ne + 2]   low 16 bits: row of the chunk the entry multiplies; high 16 bits: mask of the
+//   uint32 slot[ne + 4]   low 16 bits: row of the chunk the entry multiplies; high 16 bits: mask of the
 //                         group rows that really have the entry (all R bits set for exact groups)
 //   (pad to 16 B)
-//   T      val[ne + 2][R] the R values of the entry
+//   T      val[ne + 4][R] the R values of the entry
 //   (pad to 16 B)
-// The two extra entries are zero (slot 0, mask 0, values 0): the kernel's software pipeline prefetches up to two
+// The four extra entries are zero (slot 0, mask 0, values 0): the kernel's software pipeline prefetches up to four
 // entries past a consumer's range without a bounds check and never uses what it fetched there.
 //
 // Entries of a consumer appear in ascending column order across the chunks of a tile, i.e. a row's
@@ -68,7 +68,7 @@ struct crp_panel_host
     size_t hdr_bytes() const { return (size_t) ((3 + 2 * K + 3) / 4) * 16; }
     size_t meta_max(size_t elem) const
     {
-        return hdr_bytes() + ((((size_t) EMAX + 2) * 4 + 15) & ~(size_t) 15) + ((((size_t) EMAX + 2) * (size_t) R * elem + 15) & ~(size_t) 15);
+        return hdr_bytes() + ((((size_t) EMAX + 4) * 4 + 15) & ~(size_t) 15) + ((((size_t) EMAX + 4) * (size_t) R * elem + 15) & ~(size_t) 15);
     }
 };
 
@@ -159,7 +159,7 @@ static inline void crp_panel_fill_meta(const crp_rowgroup_host &rg, crp_panel_ho
     {
         const size_t ne = (size_t) (ph->ent_ptr[(size_t) (c + 1) * K] - ph->ent_ptr[(size_t) c * K]);
         off[c] = total;
-        total += hdr + (((ne + 2) * 4 + 15) & ~(size_t) 15) + (((ne + 2) * (size_t) R * sizeof(T) + 15) & ~(size_t) 15);
+        total += hdr + (((ne + 4) * 4 + 15) & ~(size_t) 15) + (((ne + 4) * (size_t) R * sizeof(T) + 15) & ~(size_t) 15);
     }
     off[nch] = total;
     total += hdr;               // stop record: header only
@@ -184,7 +184,7 @@ static inline void crp_panel_fill_meta(const crp_rowgroup_host &rg, crp_panel_ho
         }
         for (int w = 0; w <= K; w++) h[2 + K + w] = ph->ent_ptr[(size_t) c * K + w] - ebase;
         unsigned *slot = reinterpret_cast<unsigned *>(rec + hdr);
-        T *val = reinterpret_cast<T *>(rec + hdr + (((ne + 2) * 4 + 15) & ~(size_t) 15));
+        T *val = reinterpret_cast<T *>(rec + hdr + (((ne + 4) * 4 + 15) & ~(size_t) 15));
         for (size_t e = 0; e < ne; e++)
         {
             slot[e] = ph->ent_slot[(size_t) ebase + e];

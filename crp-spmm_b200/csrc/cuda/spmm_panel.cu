@@ -62,6 +62,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, c
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// bring [src, src + bytes) into L2 ahead of the shared-memory fill (no completion tracking); bytes a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, const unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
 {
     unsigned v;
@@ -174,6 +179,7 @@ struct panel_args
     const unsigned *chunk_need;         // per chunk: bit j = needs wait slot j (NULL: nothing to wait for)
     const unsigned *flags;              // arrival flags (one 32-bit word per rank)
     const int *wait_idx;                // wait slot -> flag index
+    int l2_prefetch;                    // pull the chunk two turns ahead into L2 (CRP_PANEL_L2PF, default 1)
     int nwait;
     int wait_all_first;                 // no wait map for this neighbour list: wait for everybody before the first chunk
     unsigned epoch;
@@ -183,11 +189,30 @@ struct panel_args
 
 // FAST: every column slice is full (n is a multiple of the slice width) and all groups are exact - no bounds predicates,
 // no mask tests in the inner loop.  The other instantiation handles partial slices and masked (relaxed-group) entries.
-template <typename T, int VEC, int R, int U, int K, bool FAST>
-__global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel_args<T> a)
+// Warp layout.  K = 8: 9 warps (producer + 8 consumers, two consumers per scheduler), 168 registers each - the register
+// file of a scheduler holds three such warps.  K = 12: 16 warps = one "producer" warpgroup (warp 0 works, warps 1 - 3 only
+// give their registers back) + three consumer warpgroups; setmaxnreg moves registers from the producer group (24 left) to the
+// consumers (160 each), so that THREE 160-register consumers fit per scheduler, evenly (3 + 1 warps on each of the four).
+// The chunk stream of a block is issued by NP producer warps in turn (chunk i by producer i % NP): one warp needs ~1000
+// cycles of dependent instructions per chunk (barrier wait, descriptor, address arithmetic, copies), which bounded the
+// whole pipeline at one chunk per ~900 cycles before.
+// SPLIT = 2: the column slice of a group is shared by two consumer warps (each keeps half of the accumulators): twice the
+// warps per scheduler at ~96 registers, for latency hiding.
+template <int K, int SPLIT = 1> struct panel_layout
 {
+    static constexpr int PW = (K == 12) ? 4 : 2;            // warps before the first consumer
+    static constexpr int NP = PW;                           // all of them issue copies
+    static constexpr int NC = K * SPLIT;                    // consumer warps
+    static constexpr int THREADS = (PW + NC) * 32;
+    static constexpr bool REBALANCE = (K == 12);
+};
+
+template <typename T, int VEC, int R, int U, int K, bool FAST, int SPLIT = 1>
+__global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel_kernel(const panel_args<T> a)
+{
+    constexpr int PW = panel_layout<K, SPLIT>::PW;
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int W = 32 * U * VEC;                         // dense columns per block
+    constexpr int W = 32 * U * VEC * SPLIT;                 // dense columns per block
     constexpr int RBW = W * (int) sizeof(T);                // bytes per staged row slice
     constexpr int HDR = ((3 + 2 * K + 3) / 4) * 16;
     constexpr unsigned FULLMASK = (1u << R) - 1u;
@@ -203,20 +228,23 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
 
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < nstage; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K); }
+        for (int s = 0; s < nstage; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K * SPLIT); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == 0)
+    if (warp < PW)
     {
+        constexpr int NP = panel_layout<K, SPLIT>::NP;
+        if (panel_layout<K, SPLIT>::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
         // ------------------------------------------------------------------ producer
         const unsigned rb = (unsigned) ncols * (unsigned) sizeof(T);
         const char *x0 = a.X0 + (size_t) col0 * sizeof(T);
         const char *x1 = a.X1 + (size_t) col0 * sizeof(T);
         unsigned seen = 0;                                  // wait slots whose flag has been observed
-        int s = 0;
+        int s = warp;                                       // this producer issues stream positions warp, warp + NP, ...
         unsigned ph = 1;                                    // parity the empty barrier of stage s is waited on
+        while (s >= nstage) { s -= nstage; ph ^= 1u; }
 
         // The chunk stream of this block: the chunks of tiles blockIdx.x, blockIdx.x + gridDim.x, ... in order, then the stop
         // record.  Descriptors are fetched TWO chunks ahead and the panel's column ids ONE chunk ahead of the chunk being
@@ -247,14 +275,43 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
             return id;
         };
         const int4 *descs = reinterpret_cast<const int4 *>(a.chunks);
-        int id0 = next_chunk(), id1 = next_chunk(), id2 = next_chunk();
+        auto next_mine = [&]() -> int {                     // the next stream position that belongs to this producer
+            int id = next_chunk();
+            #pragma unroll
+            for (int j = 1; j < NP; j++) next_chunk();
+            return id;
+        };
+        for (int j = 0; j < warp; j++) next_chunk();        // skip to this producer's first position
+        int id0 = next_mine(), id1 = next_mine(), id2 = next_mine(), id3 = next_mine();
+        if (id0 < 0) return;
+        const int4 zero4 = make_int4(0, 0, 0, 0);
         int4 d0 = __ldg(descs + id0);
-        int4 d1 = (id1 >= 0) ? __ldg(descs + id1) : make_int4(0, 0, 0, 0);
+        int4 d1 = (id1 >= 0) ? __ldg(descs + id1) : zero4;
+        int4 d2 = (id2 >= 0) ? __ldg(descs + id2) : zero4;
         int col0 = (lane < d0.y) ? __ldg(a.ucol + d0.x + lane) : 0;
+        int col1 = (id1 >= 0 && lane < d1.y) ? __ldg(a.ucol + d1.x + lane) : 0;
+        // rows [base, base + 32) of a chunk: one operation per run of rows that are consecutive in B and in memory
+        auto for_runs = [&](const int nrows_, const int base, const int mycol, auto &&op) {
+            const int r = base + lane;
+            const bool active = r < nrows_;
+            const int prev = __shfl_up_sync(0xffffffffu, mycol, 1);
+            const bool in0 = mycol < a.x0_rows;
+            const bool contig = (rb == (unsigned) RBW) && ((in0 ? a.ldx0 : a.ldx1) == (size_t) rb);
+            const bool head = active && (lane == 0 || !contig || mycol != prev + 1 || mycol == a.x0_rows);
+            const unsigned H = __ballot_sync(0xffffffffu, head);
+            const unsigned A = __ballot_sync(0xffffffffu, active);
+            if (head)
+            {
+                const unsigned above = (lane == 31) ? 0u : ((H >> (lane + 1)) << (lane + 1));
+                const int end = above ? (__ffs(above) - 1) : __popc(A);
+                const char *src = in0 ? x0 + (size_t) mycol * a.ldx0 : x1 + (size_t) (mycol - a.x0_rows) * a.ldx1;
+                op(r, src, (unsigned) (end - lane) * rb);
+            }
+        };
         while (id0 >= 0)
         {
-            const int4 d2 = (id2 >= 0) ? __ldg(descs + id2) : make_int4(0, 0, 0, 0);
-            const int col1 = (id1 >= 0 && lane < d1.y) ? __ldg(a.ucol + d1.x + lane) : 0;
+            const int4 d3 = (id3 >= 0) ? __ldg(descs + id3) : zero4;
+            const int col2 = (id2 >= 0 && lane < d2.y) ? __ldg(a.ucol + d2.x + lane) : 0;
             const int uo0 = d0.x, nrows = d0.y;
             const unsigned mo16 = (unsigned) d0.z, mbytes = (unsigned) d0.w * 16u;
             const bool is_stop = (id0 == a.nchunks);
@@ -293,31 +350,43 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
             __syncwarp();
             if (lane == 0) bulk_g2s(metas + (size_t) s * a.meta_max, a.meta + (size_t) mo16 * 16, mbytes, &full[s]);
             unsigned char *dst = rows + (size_t) s * a.CR * RBW;
-            int mycol = col0;
-            for (int r = lane; r < nrows; r += 32)
+            // One bulk copy per RUN of panel rows that are consecutive in B and in memory (leading dimension == slice width):
+            // the panel of an FEM matrix is a few long runs (the B rows of neighbouring nodes), so a chunk needs 1 - 3 copies
+            // instead of one per row.  Rows that are not contiguous in memory are copied one by one.
+            for (int base = 0; base < nrows; base += 32)
             {
-                if (r >= 32) mycol = __ldg(a.ucol + uo0 + r);
-                const char *src = (mycol < a.x0_rows) ? x0 + (size_t) mycol * a.ldx0 : x1 + (size_t) (mycol - a.x0_rows) * a.ldx1;
-                bulk_g2s(dst + (size_t) r * RBW, src, rb, &full[s]);
+                const int mycol = (base == 0) ? col0 : ((base + lane < nrows) ? __ldg(a.ucol + uo0 + base + lane) : 0);
+                for_runs(nrows, base, mycol, [&](const int r, const char *src, const unsigned bytes) { bulk_g2s(dst + (size_t) r * RBW, src, bytes, &full[s]); });
             }
-            if (++s == nstage) { s = 0; ph ^= 1u; }
-            id0 = id1;  id1 = id2;  id2 = next_chunk();
-            d0 = d1;  d1 = d2;  col0 = col1;
+            // ... and the chunk this producer issues two turns from now is pulled into L2 already (rows and record): its
+            // shared-memory fill then sees L2 latency instead of HBM latency, which the three-stage ring alone cannot cover
+            if (id2 >= 0 && a.l2_prefetch)
+            {
+                if (lane == 0 && d2.w > 0) bulk_prefetch_l2(a.meta + (size_t) (unsigned) d2.z * 16, (unsigned) d2.w * 16u);
+                for_runs(d2.y < 32 ? d2.y : 32, 0, col2, [&](const int, const char *src, const unsigned bytes) { bulk_prefetch_l2(src, bytes); });
+            }
+            s += NP;
+            while (s >= nstage) { s -= nstage; ph ^= 1u; }
+            id0 = id1;  id1 = id2;  id2 = id3;  id3 = next_mine();
+            d0 = d1;  d1 = d2;  d2 = d3;  col0 = col1;  col1 = col2;
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumers
+    if (panel_layout<K, SPLIT>::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;" ::: "memory");
     // Everything a consumer reads in its inner loop is shared memory addressed with 32-bit addresses and immediate offsets:
     // per entry one LDS (slot word, fetched two entries ahead), U 128-bit LDS of the B row slice, the R values (broadcast),
-    // R * U * VEC FMAs.  The entry lists are padded with two dummy entries (panel_build.hpp), so the software pipeline
+    // R * U * VEC FMAs.  The entry lists are padded with four dummy entries (panel_build.hpp), so the software pipeline
     // never needs a bounds check before it prefetches.
-    const int w = warp - 1;
+    const int w = (warp - PW) / SPLIT;                      // group of the tile this warp works for
+    const int half = (warp - PW) % SPLIT;                   // which part of the column slice
     constexpr int UB = 32 * VEC * (int) sizeof(T);          // bytes between a lane's consecutive column vectors
+    const int cbase = half * (32 * U * VEC) + lane * VEC;   // this lane's first column inside the slice
     bool valid[U];
     #pragma unroll
-    for (int u = 0; u < U; u++) valid[u] = FAST || ((u * 32 + lane) * VEC < ncols);
-    const unsigned rows_s = smem_u32(rows) + (unsigned) lane * VEC * (unsigned) sizeof(T);
+    for (int u = 0; u < U; u++) valid[u] = FAST || (cbase + u * 32 * VEC < ncols);
+    const unsigned rows_s = smem_u32(rows) + (unsigned) cbase * (unsigned) sizeof(T);
     const unsigned metas_s = smem_u32(metas);
 
     T acc[R][U][VEC];
@@ -328,12 +397,14 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
     {
         mbar_wait(&full[s], ph);
         const unsigned mrec = metas_s + (unsigned) s * a.meta_max;
+        // all header words at once (one shared-memory round trip), then the stop test
         const int flags = (int) lds_u32(mrec + 4);
-        if (flags & CRP_PANEL_STOP) break;
         const int e0 = (int) lds_u32(mrec + 4 * (2 + K + w)), e1 = (int) lds_u32(mrec + 4 * (3 + K + w)), ne = (int) lds_u32(mrec + 4 * (2 + 2 * K));
+        const int row0_new = (int) lds_u32(mrec + 4 * (2 + w));
+        if (flags & CRP_PANEL_STOP) break;
         if (flags & CRP_PANEL_FIRST)
         {
-            row0 = (int) lds_u32(mrec + 4 * (2 + w));
+            row0 = row0_new;
             #pragma unroll
             for (int r = 0; r < R; r++)
                 #pragma unroll
@@ -342,7 +413,7 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
                     for (int q = 0; q < VEC; q++) acc[r][u][q] = (T) 0;
         }
         const unsigned slot_a = mrec + HDR;
-        const unsigned val_a = slot_a + ((((unsigned) ne + 2u) * 4u + 15u) & ~15u);
+        const unsigned val_a = slot_a + ((((unsigned) ne + 4u) * 4u + 15u) & ~15u);
         const unsigned x_a = rows_s + (unsigned) s * (unsigned) a.CR * RBW;
 
         auto ldx = [&](const unsigned sm, T (&xv)[U][VEC]) {
@@ -379,6 +450,9 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
         };
 
         {
+            // software pipeline over the entries: the loads of entry e + 1 are issued before the FMAs of entry e, the slot words
+            // two entries ahead (measured on B200: 0.325 ms; the variant that refills a register set right after its own FMAs
+            // - no rotation - was slower, 0.343 ms: ptxas sinks those loads below the other set's FMAs anyway)
             int e = e0;
             unsigned s0 = lds_u32(slot_a + 4u * (unsigned) e), s1 = lds_u32(slot_a + 4u * (unsigned) e + 4u);
             T aa[R], ab[R], xa[U][VEC], xb[U][VEC];
@@ -406,7 +480,7 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
             #pragma unroll
             for (int r = 0; r < R; r++)
             {
-                T *crow = a.C + (size_t) (row0 + r) * a.ldc + col0 + lane * VEC;
+                T *crow = a.C + (size_t) (row0 + r) * a.ldc + col0 + cbase;
                 #pragma unroll
                 for (int u = 0; u < U; u++)
                 {
@@ -415,7 +489,7 @@ __global__ void __launch_bounds__((K + 1) * 32, 1) spmm_panel_kernel(const panel
                     if (a.beta == (T) 0)
                     {
                         #pragma unroll
-                        for (int q = 0; q < VEC; q++) out[q] = a.alpha * acc[r][u][q];
+                        for (int q = 0; q < VEC; q++) out[q] = (a.alpha == (T) 1) ? acc[r][u][q] : a.alpha * acc[r][u][q];
                     } else {
                         T old[VEC];
                         pvec<T, VEC>::ldc(crow + u * 32 * VEC, old);
@@ -456,7 +530,8 @@ void crp_panel_build(crp_spmm_plan *plan)
     const crp_rowgroup_host *rg = plan->rg_host;
     if (rg == NULL || rg->R < 2 || rg->g_row.empty() || plan->n_hint < 64) return;
     if (panel_env_int("CRP_SPMM_PANEL", 1) == 0) return;
-    const int K = 8;        // 8 consumer warps + the producer = 9 warps: two consumers per scheduler (K = 11 measured slower, round 2)
+    int K = 8;              // 8 consumer warps + the producer = 9 warps: two consumers per scheduler
+    if (panel_env_int("CRP_PANEL_K", 8) == 12 && rg->R == 6 && plan->n_hint % 256 == 0 && rg->b_mask.empty()) K = 12;   // 16 warps with register rebalancing: fp64, R = 6, n % 256 == 0
     int CR = panel_env_int("CRP_PANEL_CR", 32);
     if (CR < 4) CR = 4;
     if (CR > 64) CR = 64;
@@ -531,12 +606,12 @@ void crp_panel_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *rec
 
 // ------------------------------------------------------------------------------------- launch
 
-template <typename T, int VEC, int R, int U, int K, bool FAST>
+template <typename T, int VEC, int R, int U, int K, bool FAST, int SPLIT = 1>
 static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cudaStream_t s)
 {
     crp_panel *pn = &plan->pn;
     panel_args<T> args = args0;
-    constexpr int W = 32 * U * VEC, RBW = W * (int) sizeof(T);
+    constexpr int W = 32 * U * VEC * SPLIT, RBW = W * (int) sizeof(T);
     const crp_panel_host *ph = (const crp_panel_host *) pn->host;
     args.meta_max = (unsigned) ph->meta_max(sizeof(T));
     const size_t stage = (size_t) pn->CR * RBW + args.meta_max;
@@ -551,7 +626,7 @@ static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cu
     if (nstage < 2) return false;
     args.nstage = nstage;
     const size_t smem = CRP_PANEL_BAR_BYTES + (size_t) nstage * stage;
-    auto kern = spmm_panel_kernel<T, VEC, R, U, K, FAST>;
+    auto kern = spmm_panel_kernel<T, VEC, R, U, K, FAST, SPLIT>;
     static bool attr_set = false;
     if (!attr_set) { CRP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); attr_set = true; }
     const int nslice = (args.n + W - 1) / W;
@@ -560,7 +635,7 @@ static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cu
     if (gx_env > 0) gx = gx_env;
     if (gx < 1) gx = 1;
     if (gx > pn->ntiles) gx = pn->ntiles;
-    kern<<<dim3((unsigned) gx, (unsigned) nslice), (K + 1) * 32, smem, s>>>(args);
+    kern<<<dim3((unsigned) gx, (unsigned) nslice), panel_layout<K, SPLIT>::THREADS, smem, s>>>(args);
     CRP_LAUNCH_CHECK();
     return true;
 }
@@ -573,6 +648,16 @@ static bool panel_launch_R(crp_spmm_plan *plan, const panel_args<T> &args, cudaS
     const int U = (nv >= 128 && UMAX >= 4) ? 4 : (nv >= 64 ? 2 : 1);
     const bool fast = plan->rg.exact && (args.n % (32 * U * VEC) == 0);
 #define CRP_PN(U_) (fast ? panel_launch_cfg<T, VEC, R, U_, 8, true>(plan, args, s) : panel_launch_cfg<T, VEC, R, U_, 8, false>(plan, args, s))
+    if (plan->pn.K == 12)
+    {
+        if constexpr (R == 6 && sizeof(T) == 8 && VEC == 2) { if (fast && U == 4) return panel_launch_cfg<T, VEC, R, 4, 12, true>(plan, args, s); }
+        return false;
+    }
+    if (panel_env_int("CRP_PANEL_SPLIT", 1) == 2)
+    {
+        // experiment: 16 consumer warps (two per group), fp64 R = 6 full slices only
+        if constexpr (R == 6 && sizeof(T) == 8 && VEC == 2) { if (fast && U == 4) return panel_launch_cfg<T, VEC, R, 2, 8, true, 2>(plan, args, s); }
+    }
     if (U == 4) { if constexpr (UMAX >= 4) return CRP_PN(4); else return false; }
     if (U == 2) return CRP_PN(2);
     return CRP_PN(1);
@@ -608,6 +693,7 @@ bool crp_launch_panel(
     a.n = n;
     a.alpha = alpha;  a.beta = beta;
     a.C = C;  a.ldc = ldc;
+    a.l2_prefetch = panel_env_int("CRP_PANEL_L2PF", 1);
     if (wait != NULL && wait->nwait > 0)
     {
         if (wait->nwait > 32) return false;                 // the caller waits with the separate kernel

@@ -57,8 +57,8 @@ extern "C" int panel_emul_spmm(
             if (ck.nrows > stats[9]) stats[9] = ck.nrows;
             if (ne > stats[10]) stats[10] = ne;
             const unsigned *slots = (const unsigned *) (rec + HDR);
-            const double *vals = (const double *) (rec + HDR + ((((size_t) ne + 2) * 4 + 15) & ~(size_t) 15));
-            for (int e = ne; e < ne + 2; e++) { if (slots[e] != 0) return -22; for (int r = 0; r < R; r++) if (vals[(size_t) e * R + r] != 0.0) return -23; }
+            const double *vals = (const double *) (rec + HDR + ((((size_t) ne + 4) * 4 + 15) & ~(size_t) 15));
+            for (int e = ne; e < ne + 4; e++) { if (slots[e] != 0) return -22; for (int r = 0; r < R; r++) if (vals[(size_t) e * R + r] != 0.0) return -23; }
             const int *ucol = ph.ucol.data() + ck.uo0;
             for (int r = 1; r < ck.nrows; r++) if (ucol[r] <= ucol[r - 1]) return -16;     // panel rows strictly ascending
             for (int w = 0; w < K; w++)
