@@ -42,6 +42,7 @@ WORKLOADS = {
     "er":      ("erdos_renyi", {"scale": 22, "nnz_per_row": 16}, 64, "f64", "rp", "Erdos-Renyi 4M x 4M, 16 nnz/row (BASELINE configs[2])"),
     "rmat":    ("rmat", {"scale": 22, "edge_factor": 32}, 128, "f64", "2d", "RMAT scale 22, edge factor 32 (BASELINE configs[3])"),
     "stencil": ("stencil27", {"n": 128}, 1024, "f32", "2d", "27-point stencil 128^3, n=1024 fp32 (BASELINE configs[4])"),
+    "er2d":    ("erdos_renyi", {"scale": 22, "nnz_per_row": 16}, 64, "f64", "2d", "Erdos-Renyi 4M x 4M, 16 nnz/row through the 2-D engine (grid from the cost model; exercises replicate-A)"),
     "pwtk_small": ("pwtk_like", {"m": 20000, "target_nnz": 1060000, "bandwidth": 17000, "grid_w": 32}, 64, "f64", "2d", "small pwtk-shaped test matrix"),
 }
 
@@ -49,7 +50,8 @@ WORKLOADS = {
 def matrix_path(workload):
     """Binary CSR of the workload, generated once per box (rank 0) into the temp dir."""
     gname, kw, *_ = WORKLOADS[workload]
-    path = os.path.join(tempfile.gettempdir(), f"crp_bench_{workload}.bin")
+    key = gname + "".join(f"_{k}{v}" for k, v in sorted(kw.items()))         # workloads that share a matrix share the file
+    path = os.path.join(tempfile.gettempdir(), f"crp_bench_{key}.bin")
     if not os.path.exists(path):
         from pycrp import gen
         m, k, rp, ci, v = getattr(gen, gname)(**kw)

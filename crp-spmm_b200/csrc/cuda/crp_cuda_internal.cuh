@@ -108,6 +108,19 @@ struct crp_spmm_wait
     int       *err;             // pinned host word set on timeout
 };
 
+// the B rows this rank owes its neighbours (peer-memory transport): stored by the SpMM kernel itself when it can
+struct crp_spmm_put
+{
+    int       nrow;             // rows to send (may be 0: only the flags are published)
+    size_t    row_bytes;
+    const int *ridx;            // device: row of X0 for each
+    void *const *dst_rows;      // device: destination address of each (peer memory)
+    unsigned int *const *flag_ptrs;   // device: this rank's arrival flag on each neighbour
+    int       nflag;
+    unsigned  epoch;
+    unsigned int *counter;      // device word, zero between launches
+};
+
 struct crp_spmm_plan
 {
     int       m, k;

@@ -62,11 +62,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, c
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// bring [src, src + bytes) into L2 ahead of the shared-memory fill (no completion tracking); bytes a multiple of 16
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, const unsigned bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src_gmem), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
 {
     unsigned v;
@@ -87,6 +82,7 @@ template <> struct pvec<double, 2>
     static __device__ __forceinline__ void lds_s(const unsigned addr, double (&v)[2]) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr)); }
     static __device__ __forceinline__ void lds(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
     static __device__ __forceinline__ void ldc(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void ldg(const double *p, double (&v)[2]) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y; }
     static __device__ __forceinline__ void st(double *p, const double (&v)[2]) { __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1])); }
 };
 template <> struct pvec<float, 4>
@@ -94,6 +90,7 @@ template <> struct pvec<float, 4>
     static __device__ __forceinline__ void lds_s(const unsigned addr, float (&v)[4]) { asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr)); }
     static __device__ __forceinline__ void lds(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     static __device__ __forceinline__ void ldc(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void ldg(const float *p, float (&v)[4]) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     static __device__ __forceinline__ void st(float *p, const float (&v)[4]) { __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3])); }
 };
 
@@ -162,7 +159,7 @@ enum { CRP_PANEL_MAXSTAGE = 8, CRP_PANEL_BAR_BYTES = 128 };
 template <typename T>
 struct panel_args
 {
-    const int *tile_chunk_ptr;          // ntiles + 1
+    const int2 *tile_ranges;            // ntiles: chunk range of the tile at each position of the processing order
     const crp_panel_chunk *chunks;      // nchunks + 1 (stop record last)
     const int *ucol;
     const unsigned char *meta;
@@ -179,7 +176,20 @@ struct panel_args
     const unsigned *chunk_need;         // per chunk: bit j = needs wait slot j (NULL: nothing to wait for)
     const unsigned *flags;              // arrival flags (one 32-bit word per rank)
     const int *wait_idx;                // wait slot -> flag index
-    int l2_prefetch;                    // pull the chunk two turns ahead into L2 (CRP_PANEL_L2PF, default 1)
+    // rows that are in no group ("rest" rows: the cut nodes at a rank's first / last row, irregular rows): multiplied inside
+    // this kernel by one extra warp per block straight from the CSR arrays, so that a handful of rows does not cost a launch
+    int nrest;                          // 0: none (or the caller runs the row-split kernel for them)
+    const int *rest_rows;
+    const int *rowptr;  const int *colidx;  const T *val;
+    // multi-GPU, fused exchange: every block first stores its share of the B rows the neighbours need straight into their
+    // receive buffers (NVLink), the last block to finish publishes this rank's arrival flag on every neighbour
+    int put_nrow;                       // 0: nothing to put
+    unsigned put_row_bytes;             // multiple of 16
+    const int *put_ridx;                // rows of X0 to send
+    char *const *put_dst_rows;          // destination of each (peer memory)
+    unsigned int *const *put_flag_ptrs; // this rank's flag on each neighbour
+    int put_nflag;
+    unsigned int *put_counter;          // blocks that have finished their share (reset by the last one)
     int nwait;
     int wait_all_first;                 // no wait map for this neighbour list: wait for everybody before the first chunk
     unsigned epoch;
@@ -189,30 +199,23 @@ struct panel_args
 
 // FAST: every column slice is full (n is a multiple of the slice width) and all groups are exact - no bounds predicates,
 // no mask tests in the inner loop.  The other instantiation handles partial slices and masked (relaxed-group) entries.
-// Warp layout.  K = 8: 9 warps (producer + 8 consumers, two consumers per scheduler), 168 registers each - the register
-// file of a scheduler holds three such warps.  K = 12: 16 warps = one "producer" warpgroup (warp 0 works, warps 1 - 3 only
-// give their registers back) + three consumer warpgroups; setmaxnreg moves registers from the producer group (24 left) to the
-// consumers (160 each), so that THREE 160-register consumers fit per scheduler, evenly (3 + 1 warps on each of the four).
-// The chunk stream of a block is issued by NP producer warps in turn (chunk i by producer i % NP): one warp needs ~1000
-// cycles of dependent instructions per chunk (barrier wait, descriptor, address arithmetic, copies), which bounded the
-// whole pipeline at one chunk per ~900 cycles before.
-// SPLIT = 2: the column slice of a group is shared by two consumer warps (each keeps half of the accumulators): twice the
-// warps per scheduler at ~96 registers, for latency hiding.
-template <int K, int SPLIT = 1> struct panel_layout
+// Warp layout of a block: NP producer warps (chunk i of the block's stream is issued by producer i % NP - one warp needs
+// ~1000 cycles of dependent instructions per chunk, which bounded the pipeline before), K consumer warps (one row group of
+// the tile each; 168 registers: the register file of a scheduler holds three such warps), one warp for the rows that are in
+// no group.  Measured and dropped in round 2 (profiles/r02_kernel_sweep.md): K = 11 / 12 consumers (with setmaxnreg register
+// rebalancing) and two half-width warps per group - more warps per scheduler did not help, the shared-memory pipe is the limit.
+template <int K> struct panel_layout
 {
-    static constexpr int PW = (K == 12) ? 4 : 2;            // warps before the first consumer
-    static constexpr int NP = PW;                           // all of them issue copies
-    static constexpr int NC = K * SPLIT;                    // consumer warps
-    static constexpr int THREADS = (PW + NC) * 32;
-    static constexpr bool REBALANCE = (K == 12);
+    static constexpr int NP = 2;                            // producer warps = warps before the first consumer
+    static constexpr int THREADS = (NP + K + 1) * 32;
 };
 
-template <typename T, int VEC, int R, int U, int K, bool FAST, int SPLIT = 1>
-__global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel_kernel(const panel_args<T> a)
+template <typename T, int VEC, int R, int U, int K, bool FAST>
+__global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel(const panel_args<T> a)
 {
-    constexpr int PW = panel_layout<K, SPLIT>::PW;
+    constexpr int PW = panel_layout<K>::NP;
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int W = 32 * U * VEC * SPLIT;                 // dense columns per block
+    constexpr int W = 32 * U * VEC;                         // dense columns per block
     constexpr int RBW = W * (int) sizeof(T);                // bytes per staged row slice
     constexpr int HDR = ((3 + 2 * K + 3) / 4) * 16;
     constexpr unsigned FULLMASK = (1u << R) - 1u;
@@ -228,15 +231,39 @@ __global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel
 
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < nstage; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K * SPLIT); }
+        for (int s = 0; s < nstage; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (a.put_nflag > 0)
+    {
+        // fused "pack + send" (reference src/rowpara_spmm.c:232-301): 128-bit loads of the own B rows, 128-bit stores over NVLink
+        const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned vpr = a.put_row_bytes / 16u;
+        const size_t total = (size_t) a.put_nrow * vpr;
+        for (size_t t = (size_t) bid * blockDim.x + threadIdx.x; t < total; t += (size_t) nblocks * blockDim.x)
+        {
+            const unsigned r = (unsigned) (t / vpr), v = (unsigned) (t - (size_t) r * vpr);
+            const uint4 val = *reinterpret_cast<const uint4 *>(a.X0 + (size_t) a.put_ridx[r] * a.ldx0 + (size_t) v * 16);
+            *reinterpret_cast<uint4 *>(a.put_dst_rows[r] + (size_t) v * 16) = val;
+        }
+        __threadfence_system();
+    }
     __syncthreads();
+    if (a.put_nflag > 0 && threadIdx.x == 0)
+    {
+        const unsigned nblocks = gridDim.x * gridDim.y;
+        if (atomicAdd(a.put_counter, 1u) == nblocks - 1u)
+        {
+            __threadfence();                    // the other blocks' stores (fenced before their atomicAdd) come before the flags
+            for (int j = 0; j < a.put_nflag; j++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.put_flag_ptrs[j]), "r"(a.epoch) : "memory");
+            *a.put_counter = 0u;
+        }
+    }
 
     if (warp < PW)
     {
-        constexpr int NP = panel_layout<K, SPLIT>::NP;
-        if (panel_layout<K, SPLIT>::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+        constexpr int NP = panel_layout<K>::NP;
         // ------------------------------------------------------------------ producer
         const unsigned rb = (unsigned) ncols * (unsigned) sizeof(T);
         const char *x0 = a.X0 + (size_t) col0 * sizeof(T);
@@ -252,8 +279,8 @@ __global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel
         // critical path: while the producer sleeps on an empty barrier they complete.  (Round-2 ncu of the first version, which
         // loaded them in the iteration that used them: consumers spent 29 % of their samples waiting for the full barrier.)
         int it_t = blockIdx.x, it_c = -1, it_cend = -1, nx_c = -1, nx_cend = -1;
-        if (it_t < a.ntiles) { it_c = __ldg(a.tile_chunk_ptr + it_t); it_cend = __ldg(a.tile_chunk_ptr + it_t + 1); }
-        if (it_t + (int) gridDim.x < a.ntiles) { nx_c = __ldg(a.tile_chunk_ptr + it_t + gridDim.x); nx_cend = __ldg(a.tile_chunk_ptr + it_t + gridDim.x + 1); }
+        if (it_t < a.ntiles) { const int2 tr = __ldg(a.tile_ranges + it_t); it_c = tr.x; it_cend = tr.y; }
+        if (it_t + (int) gridDim.x < a.ntiles) { const int2 tr = __ldg(a.tile_ranges + it_t + gridDim.x); nx_c = tr.x; nx_cend = tr.y; }
         bool stop_given = false;
         auto next_chunk = [&]() -> int {                    // next chunk id of the stream; a.nchunks = stop record; -1 = past the end
             if (it_c < 0)
@@ -269,7 +296,7 @@ __global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel
                 if (it_t < a.ntiles)
                 {
                     it_c = nx_c;  it_cend = nx_cend;
-                    if (it_t + (int) gridDim.x < a.ntiles) { nx_c = __ldg(a.tile_chunk_ptr + it_t + gridDim.x); nx_cend = __ldg(a.tile_chunk_ptr + it_t + gridDim.x + 1); }
+                    if (it_t + (int) gridDim.x < a.ntiles) { const int2 tr = __ldg(a.tile_ranges + it_t + gridDim.x); nx_c = tr.x; nx_cend = tr.y; }
                 } else it_c = -1;
             }
             return id;
@@ -311,7 +338,7 @@ __global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel
         while (id0 >= 0)
         {
             const int4 d3 = (id3 >= 0) ? __ldg(descs + id3) : zero4;
-            const int col2 = (id2 >= 0 && lane < d2.y) ? __ldg(a.ucol + d2.x + lane) : 0;
+            const int col2 = (id2 >= 0 && lane < d2.y) ? __ldg(a.ucol + d2.x + lane) : 0;      // column ids two turns ahead
             const int uo0 = d0.x, nrows = d0.y;
             const unsigned mo16 = (unsigned) d0.z, mbytes = (unsigned) d0.w * 16u;
             const bool is_stop = (id0 == a.nchunks);
@@ -358,13 +385,6 @@ __global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel
                 const int mycol = (base == 0) ? col0 : ((base + lane < nrows) ? __ldg(a.ucol + uo0 + base + lane) : 0);
                 for_runs(nrows, base, mycol, [&](const int r, const char *src, const unsigned bytes) { bulk_g2s(dst + (size_t) r * RBW, src, bytes, &full[s]); });
             }
-            // ... and the chunk this producer issues two turns from now is pulled into L2 already (rows and record): its
-            // shared-memory fill then sees L2 latency instead of HBM latency, which the three-stage ring alone cannot cover
-            if (id2 >= 0 && a.l2_prefetch)
-            {
-                if (lane == 0 && d2.w > 0) bulk_prefetch_l2(a.meta + (size_t) (unsigned) d2.z * 16, (unsigned) d2.w * 16u);
-                for_runs(d2.y < 32 ? d2.y : 32, 0, col2, [&](const int, const char *src, const unsigned bytes) { bulk_prefetch_l2(src, bytes); });
-            }
             s += NP;
             while (s >= nstage) { s -= nstage; ph ^= 1u; }
             id0 = id1;  id1 = id2;  id2 = id3;  id3 = next_mine();
@@ -373,16 +393,107 @@ __global__ void __launch_bounds__(panel_layout<K, SPLIT>::THREADS, 1) spmm_panel
         return;
     }
 
+    // ---------------------------------------------------------------------- rest rows
+    if (warp == PW + K)
+    {
+        if (a.nrest <= 0) return;
+        if (a.nwait > 0)
+        {
+            // a rest row may read received rows: all neighbours first (plain loads follow, no async-proxy fence needed)
+            if (lane < a.nwait)
+            {
+                const unsigned *f = a.flags + a.wait_idx[lane];
+                long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                while ((int) (ld_acquire_sys(f) - a.epoch) < 0)
+                {
+                    long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > a.timeout_ns) { *a.err = 1; break; }
+                    __nanosleep(100);
+                }
+            }
+            __syncwarp();
+        }
+        constexpr int UT = W / (32 * VEC);                  // this warp covers the block's whole column slice
+        constexpr int NZ = 4;
+        const T *X0 = reinterpret_cast<const T *>(a.X0) + col0 + lane * VEC;
+        const T *X1 = reinterpret_cast<const T *>(a.X1) + col0 + lane * VEC;
+        const size_t ld0 = a.ldx0 / sizeof(T), ld1 = a.ldx1 / sizeof(T);
+        bool ok[UT];
+        #pragma unroll
+        for (int u = 0; u < UT; u++) ok[u] = (lane * VEC + u * 32 * VEC) < ncols;
+        for (int i = blockIdx.x; i < a.nrest; i += gridDim.x)
+        {
+            const int row = __ldg(a.rest_rows + i);
+            const int pb = __ldg(a.rowptr + row), pe = __ldg(a.rowptr + row + 1);
+            T acc[UT][VEC];
+            #pragma unroll
+            for (int u = 0; u < UT; u++)
+                #pragma unroll
+                for (int q = 0; q < VEC; q++) acc[u][q] = (T) 0;
+            for (int p = pb; p < pe; p += NZ)
+            {
+                int c[NZ];  T v[NZ];  T x[NZ][UT][VEC];
+                #pragma unroll
+                for (int j = 0; j < NZ; j++)
+                {
+                    const bool in = p + j < pe;
+                    c[j] = in ? __ldg(a.colidx + p + j) : 0;
+                    v[j] = in ? __ldg(a.val + p + j) : (T) 0;
+                }
+                #pragma unroll
+                for (int j = 0; j < NZ; j++)
+                {
+                    const T *xr = (c[j] < a.x0_rows) ? X0 + (size_t) c[j] * ld0 : X1 + (size_t) (c[j] - a.x0_rows) * ld1;
+                    #pragma unroll
+                    for (int u = 0; u < UT; u++)
+                    {
+                        if (ok[u] && p + j < pe) pvec<T, VEC>::ldg(xr + u * 32 * VEC, x[j][u]);
+                        else { for (int q = 0; q < VEC; q++) x[j][u][q] = (T) 0; }
+                    }
+                }
+                #pragma unroll
+                for (int j = 0; j < NZ; j++)
+                    if (p + j < pe)
+                    {
+                        #pragma unroll
+                        for (int u = 0; u < UT; u++)
+                            #pragma unroll
+                            for (int q = 0; q < VEC; q++) acc[u][q] = fma(v[j], x[j][u][q], acc[u][q]);
+                    }
+            }
+            if (pb == pe && a.beta == (T) 1) continue;
+            T *crow = a.C + (size_t) row * a.ldc + col0 + lane * VEC;
+            #pragma unroll
+            for (int u = 0; u < UT; u++)
+            {
+                if (!ok[u]) continue;
+                T out[VEC];
+                if (a.beta == (T) 0)
+                {
+                    #pragma unroll
+                    for (int q = 0; q < VEC; q++) out[q] = a.alpha * acc[u][q];
+                } else {
+                    T old[VEC];
+                    pvec<T, VEC>::ldc(crow + u * 32 * VEC, old);
+                    #pragma unroll
+                    for (int q = 0; q < VEC; q++) out[q] = fma(a.alpha, acc[u][q], a.beta * old[q]);
+                }
+                pvec<T, VEC>::st(crow + u * 32 * VEC, out);
+            }
+        }
+        return;
+    }
+
     // ---------------------------------------------------------------------- consumers
-    if (panel_layout<K, SPLIT>::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;" ::: "memory");
     // Everything a consumer reads in its inner loop is shared memory addressed with 32-bit addresses and immediate offsets:
     // per entry one LDS (slot word, fetched two entries ahead), U 128-bit LDS of the B row slice, the R values (broadcast),
     // R * U * VEC FMAs.  The entry lists are padded with four dummy entries (panel_build.hpp), so the software pipeline
     // never needs a bounds check before it prefetches.
-    const int w = (warp - PW) / SPLIT;                      // group of the tile this warp works for
-    const int half = (warp - PW) % SPLIT;                   // which part of the column slice
+    const int w = warp - PW;                                // group of the tile this warp works for
     constexpr int UB = 32 * VEC * (int) sizeof(T);          // bytes between a lane's consecutive column vectors
-    const int cbase = half * (32 * U * VEC) + lane * VEC;   // this lane's first column inside the slice
+    const int cbase = lane * VEC;                           // this lane's first column inside the slice
     bool valid[U];
     #pragma unroll
     for (int u = 0; u < U; u++) valid[u] = FAST || (cbase + u * 32 * VEC < ncols);
@@ -530,8 +641,7 @@ void crp_panel_build(crp_spmm_plan *plan)
     const crp_rowgroup_host *rg = plan->rg_host;
     if (rg == NULL || rg->R < 2 || rg->g_row.empty() || plan->n_hint < 64) return;
     if (panel_env_int("CRP_SPMM_PANEL", 1) == 0) return;
-    int K = 8;              // 8 consumer warps + the producer = 9 warps: two consumers per scheduler
-    if (panel_env_int("CRP_PANEL_K", 8) == 12 && rg->R == 6 && plan->n_hint % 256 == 0 && rg->b_mask.empty()) K = 12;   // 16 warps with register rebalancing: fp64, R = 6, n % 256 == 0
+    const int K = 8;        // groups per tile = consumer warps (two per scheduler)
     int CR = panel_env_int("CRP_PANEL_CR", 32);
     if (CR < 4) CR = 4;
     if (CR > 64) CR = 64;
@@ -542,7 +652,9 @@ void crp_panel_build(crp_spmm_plan *plan)
     pn->host = ph;
     pn->K = K;  pn->CR = CR;  pn->EMAX = EMAX;  pn->R = rg->R;
     pn->ntiles = ph->ntiles;  pn->nchunks = ph->nchunks();  pn->union_rows = (long long) ph->ucol.size();
-    pn->d_tile_chunk_ptr = (int *) panel_upload(ph->tile_chunk_ptr.data(), sizeof(int) * ph->tile_chunk_ptr.size());
+    std::vector<int> ranges((size_t) 2 * ph->ntiles);
+    for (int t = 0; t < ph->ntiles; t++) { ranges[2 * t] = ph->tile_chunk_ptr[t]; ranges[2 * t + 1] = ph->tile_chunk_ptr[t + 1]; }
+    pn->d_tile_chunk_ptr = (int *) panel_upload(ranges.data(), sizeof(int) * ranges.size());
     pn->d_ucol = (int *) panel_upload(ph->ucol.data(), sizeof(int) * ph->ucol.size());
 }
 
@@ -602,23 +714,39 @@ void crp_panel_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *rec
     }
     if (any) pn->d_chunk_need = (unsigned *) panel_upload(need.data(), sizeof(unsigned) * need.size());
     pn->nslot = nslot;
+    // processing order: tiles that only read the rank's own B rows first, tiles that read received rows last - the exchange
+    // is then hidden behind the local part of the product inside the one kernel
+    std::vector<int> ranges;
+    ranges.reserve((size_t) 2 * ph->ntiles);
+    for (int pass = 0; pass < 2; pass++)
+        for (int t = 0; t < ph->ntiles; t++)
+        {
+            bool remote = false;
+            for (int c = ph->tile_chunk_ptr[t]; c < ph->tile_chunk_ptr[t + 1]; c++) remote = remote || need[c] != 0;
+            if ((int) remote == pass) { ranges.push_back(ph->tile_chunk_ptr[t]); ranges.push_back(ph->tile_chunk_ptr[t + 1]); }
+        }
+    CRP_CUDA_CHECK(cudaMemcpy(pn->d_tile_chunk_ptr, ranges.data(), sizeof(int) * ranges.size(), cudaMemcpyHostToDevice));
 }
 
 // ------------------------------------------------------------------------------------- launch
 
-template <typename T, int VEC, int R, int U, int K, bool FAST, int SPLIT = 1>
+template <typename T, int VEC, int R, int U, int K, bool FAST>
 static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cudaStream_t s)
 {
     crp_panel *pn = &plan->pn;
     panel_args<T> args = args0;
-    constexpr int W = 32 * U * VEC * SPLIT, RBW = W * (int) sizeof(T);
+    constexpr int W = 32 * U * VEC, RBW = W * (int) sizeof(T);
     const crp_panel_host *ph = (const crp_panel_host *) pn->host;
     args.meta_max = (unsigned) ph->meta_max(sizeof(T));
     const size_t stage = (size_t) pn->CR * RBW + args.meta_max;
-    int dev = 0, smem_max = 0, nsm = 0;
-    CRP_CUDA_CHECK(cudaGetDevice(&dev));
-    CRP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    CRP_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    static int smem_max = 0, nsm = 0;          // one device per process
+    if (nsm == 0)
+    {
+        int dev = 0;
+        CRP_CUDA_CHECK(cudaGetDevice(&dev));
+        CRP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        CRP_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    }
     int nstage = (int) (((size_t) smem_max - CRP_PANEL_BAR_BYTES) / stage);
     if (nstage > CRP_PANEL_MAXSTAGE) nstage = CRP_PANEL_MAXSTAGE;
     const int want = panel_env_int("CRP_PANEL_STAGES", 0);
@@ -626,7 +754,7 @@ static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cu
     if (nstage < 2) return false;
     args.nstage = nstage;
     const size_t smem = CRP_PANEL_BAR_BYTES + (size_t) nstage * stage;
-    auto kern = spmm_panel_kernel<T, VEC, R, U, K, FAST, SPLIT>;
+    auto kern = spmm_panel_kernel<T, VEC, R, U, K, FAST>;
     static bool attr_set = false;
     if (!attr_set) { CRP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); attr_set = true; }
     const int nslice = (args.n + W - 1) / W;
@@ -635,7 +763,7 @@ static bool panel_launch_cfg(crp_spmm_plan *plan, const panel_args<T> &args0, cu
     if (gx_env > 0) gx = gx_env;
     if (gx < 1) gx = 1;
     if (gx > pn->ntiles) gx = pn->ntiles;
-    kern<<<dim3((unsigned) gx, (unsigned) nslice), panel_layout<K, SPLIT>::THREADS, smem, s>>>(args);
+    kern<<<dim3((unsigned) gx, (unsigned) nslice), panel_layout<K>::THREADS, smem, s>>>(args);
     CRP_LAUNCH_CHECK();
     return true;
 }
@@ -648,16 +776,6 @@ static bool panel_launch_R(crp_spmm_plan *plan, const panel_args<T> &args, cudaS
     const int U = (nv >= 128 && UMAX >= 4) ? 4 : (nv >= 64 ? 2 : 1);
     const bool fast = plan->rg.exact && (args.n % (32 * U * VEC) == 0);
 #define CRP_PN(U_) (fast ? panel_launch_cfg<T, VEC, R, U_, 8, true>(plan, args, s) : panel_launch_cfg<T, VEC, R, U_, 8, false>(plan, args, s))
-    if (plan->pn.K == 12)
-    {
-        if constexpr (R == 6 && sizeof(T) == 8 && VEC == 2) { if (fast && U == 4) return panel_launch_cfg<T, VEC, R, 4, 12, true>(plan, args, s); }
-        return false;
-    }
-    if (panel_env_int("CRP_PANEL_SPLIT", 1) == 2)
-    {
-        // experiment: 16 consumer warps (two per group), fp64 R = 6 full slices only
-        if constexpr (R == 6 && sizeof(T) == 8 && VEC == 2) { if (fast && U == 4) return panel_launch_cfg<T, VEC, R, 2, 8, true, 2>(plan, args, s); }
-    }
     if (U == 4) { if constexpr (UMAX >= 4) return CRP_PN(4); else return false; }
     if (U == 2) return CRP_PN(2);
     return CRP_PN(1);
@@ -666,14 +784,17 @@ static bool panel_launch_R(crp_spmm_plan *plan, const panel_args<T> &args, cudaS
 
 // false: the panel form does not apply to this call (no panel, misaligned operands, narrow n) - the caller falls back
 // to the row-group kernel.  wait != NULL: the kernel itself waits for the neighbours' arrival flags (peer-memory transport).
+// *rest_done (out): the kernel also multiplied the rows that are in no group (true) or the caller still has to (false)
 template <typename T, int VEC>
 bool crp_launch_panel(
-    crp_spmm_plan *plan, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc,
-    const crp_spmm_wait *wait, cudaStream_t s
+    crp_spmm_plan *plan, const T *val, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc,
+    const crp_spmm_wait *wait, const crp_spmm_put *put, bool *rest_done, cudaStream_t s
 )
 {
+    *rest_done = false;
     crp_panel *pn = &plan->pn;
     if (pn->host == NULL || pn->ntiles == 0) return false;
+    if (put != NULL && (put->row_bytes % 16 != 0 || ((uintptr_t) X0 & 15) != 0)) return false;       // the fused put moves 16-byte units
     const size_t es = sizeof(T);
     if (n < 64 || (n * es) % 16 != 0 || (ldx0 * es) % 16 != 0 || (X1 != NULL && (ldx1 * es) % 16 != 0) || (ldc * es) % 16 != 0) return false;
     if ((((uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C) & 15) != 0) return false;
@@ -681,7 +802,7 @@ bool crp_launch_panel(
     const int slot = (es == 8) ? 0 : 1;
     panel_args<T> a;
     memset(&a, 0, sizeof(a));
-    a.tile_chunk_ptr = pn->d_tile_chunk_ptr;
+    a.tile_ranges = (const int2 *) pn->d_tile_chunk_ptr;
     a.chunks = (const crp_panel_chunk *) pn->d_chunks[slot];
     a.ucol = pn->d_ucol;
     a.meta = pn->d_meta[slot];
@@ -693,7 +814,13 @@ bool crp_launch_panel(
     a.n = n;
     a.alpha = alpha;  a.beta = beta;
     a.C = C;  a.ldc = ldc;
-    a.l2_prefetch = panel_env_int("CRP_PANEL_L2PF", 1);
+    // few rest rows without very long ones: the kernel's extra warp takes them (one row per block and turn)
+    if (plan->rg.nrest > 0 && plan->rg.nrest <= 2048 && plan->lr.nlong == 0 && panel_env_int("CRP_PANEL_REST", 1))
+    {
+        a.nrest = plan->rg.nrest;  a.rest_rows = plan->rg.d_rest;
+        a.rowptr = plan->d_rowptr;  a.colidx = plan->d_colidx;  a.val = val;
+        *rest_done = true;
+    }
     if (wait != NULL && wait->nwait > 0)
     {
         if (wait->nwait > 32) return false;                 // the caller waits with the separate kernel
@@ -701,6 +828,12 @@ bool crp_launch_panel(
         a.wait_all_first = (pn->nslot == wait->nwait) ? 0 : 1;
         a.flags = wait->flags;  a.wait_idx = wait->wait_idx;  a.nwait = wait->nwait;
         a.epoch = wait->epoch;  a.timeout_ns = wait->timeout_ns;  a.err = wait->err;
+    }
+    if (put != NULL && put->nflag > 0)
+    {
+        a.put_nrow = put->nrow;  a.put_row_bytes = (unsigned) put->row_bytes;  a.put_ridx = put->ridx;
+        a.put_dst_rows = (char *const *) put->dst_rows;  a.put_flag_ptrs = put->flag_ptrs;  a.put_nflag = put->nflag;
+        a.put_counter = put->counter;  a.epoch = put->epoch;
     }
     switch (pn->R)
     {
@@ -713,5 +846,5 @@ bool crp_launch_panel(
     }
 }
 
-template bool crp_launch_panel<double, 2>(crp_spmm_plan *, const int, const double *, size_t, const double *, size_t, double, double, double *, size_t, const crp_spmm_wait *, cudaStream_t);
-template bool crp_launch_panel<float, 4>(crp_spmm_plan *, const int, const float *, size_t, const float *, size_t, float, float, float *, size_t, const crp_spmm_wait *, cudaStream_t);
+template bool crp_launch_panel<double, 2>(crp_spmm_plan *, const double *, const int, const double *, size_t, const double *, size_t, double, double, double *, size_t, const crp_spmm_wait *, const crp_spmm_put *, bool *, cudaStream_t);
+template bool crp_launch_panel<float, 4>(crp_spmm_plan *, const float *, const int, const float *, size_t, const float *, size_t, float, float, float *, size_t, const crp_spmm_wait *, const crp_spmm_put *, bool *, cudaStream_t);

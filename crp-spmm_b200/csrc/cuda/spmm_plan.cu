@@ -20,8 +20,8 @@ bool crp_launch_mergepath(
 );
 template <typename T, int VEC>
 bool crp_launch_panel(
-    crp_spmm_plan *plan, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc,
-    const crp_spmm_wait *wait, cudaStream_t s
+    crp_spmm_plan *plan, const T *val, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc,
+    const crp_spmm_wait *wait, const crp_spmm_put *put, bool *rest_done, cudaStream_t s
 );
 template <typename T, int VEC>
 void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
@@ -130,7 +130,7 @@ static void wait_first(const crp_spmm_wait *wait, cudaStream_t s)
 template <typename T, int VECN>
 static void spmm_dispatch(
     crp_spmm_plan *plan, const T *val, const T *bval, const int n, const T *X0, size_t ldx0, const T *X1, size_t ldx1,
-    T alpha, T beta, T *C, size_t ldc, const crp_spmm_wait *wait, cudaStream_t s, const char *tname
+    T alpha, T beta, T *C, size_t ldc, const crp_spmm_wait *wait, const crp_spmm_put *put, const int n_elem_size, cudaStream_t s, const char *tname
 )
 {
     const int x0_rows = plan->x0_rows;
@@ -142,14 +142,19 @@ static void spmm_dispatch(
     {
         // the panel kernel waits for the neighbours itself (and for all of them before it ends), so the rest rows,
         // which may read received rows too, follow it on the stream
-        if (crp_launch_panel<T, VECN>(plan, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, wait, s))
+        bool rest_done = false;
+        if (crp_launch_panel<T, VECN>(plan, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, wait, put, &rest_done, s))
         {
-            if (rg->nrest > 0) rowsplit_balanced<T, VECN>(plan, true, rg->nrest, rg->d_rest, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s);
-            snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_panel_%s_R%d_K%d%s%s", tname, rg->R, plan->pn.K, rg->nrest > 0 ? "+rowsplit" : "", rg->nrest > 0 ? lr_tag : "");
+            const bool rest_sep = rg->nrest > 0 && !rest_done;
+            if (rest_sep) rowsplit_balanced<T, VECN>(plan, true, rg->nrest, rg->d_rest, val, n, X0, ldx0, X1, ldx1, alpha, beta, C, ldc, s);
+            snprintf(plan->kernel_name, sizeof(plan->kernel_name), "spmm_panel_%s_R%d_K%d%s%s", tname, rg->R, plan->pn.K, rest_sep ? "+rowsplit" : "", rest_sep ? lr_tag : "");
             plan->last_kernel = plan->kernel_name;
             return;
         }
     }
+    // the other kernels neither put nor wait themselves: separate launches first
+    if (put != NULL && put->nflag > 0)
+        crp_cuda_put_rows_signal((size_t) n_elem_size, put->nrow, n, X0, (int) ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, (void *) s);
     wait_first(wait, s);
     // nnz-balanced kernel: forced, or chosen for matrices without row groups whose longest row is far above the average
     // (power-law graphs: one-row-per-warp leaves most warps idle behind the hubs)
@@ -190,6 +195,35 @@ extern "C" void crp_cuda_spmm_exec(
     crp_cuda_spmm_exec_wait(plan, n, elem_size, alpha, X0, ldx0, X1, ldx1, beta, C, ldc, NULL, NULL, 0, 0, 0.0, NULL, stream);
 }
 
+static void spmm_exec_common(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha, const void *X0, const int ldx0, const void *X1, const int ldx1,
+    const double beta, void *C, const int ldc, const crp_spmm_wait *wait, const crp_spmm_put *put, cudaStream_t s
+);
+
+extern "C" void crp_cuda_spmm_exec_exchange(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
+    const void *X0, const int ldx0, const void *X1, const int ldx1, const double beta, void *C, const int ldc,
+    const crp_exchange *xc, void *stream
+)
+{
+    if (plan == NULL) { fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: NULL plan\n"); abort(); }
+    crp_spmm_wait wt, *wait = NULL;
+    crp_spmm_put pt, *put = NULL;
+    if (xc != NULL && xc->nwait > 0)
+    {
+        wt.flags = xc->flags_d;  wt.wait_idx = xc->wait_idx_d;  wt.nwait = xc->nwait;  wt.epoch = xc->epoch;
+        wt.timeout_ns = (long long) (xc->timeout_s * 1e9);  wt.err = xc->err;
+        wait = &wt;
+    }
+    if (xc != NULL && xc->nflag > 0)
+    {
+        pt.nrow = xc->n_send_rows;  pt.row_bytes = (size_t) elem_size * (size_t) n;  pt.ridx = xc->send_ridx_d;  pt.dst_rows = xc->dst_rows_d;
+        pt.flag_ptrs = xc->flag_ptrs_d;  pt.nflag = xc->nflag;  pt.epoch = xc->epoch;  pt.counter = xc->done_counter_d;
+        put = &pt;
+    }
+    spmm_exec_common(plan, n, elem_size, alpha, X0, ldx0, X1, ldx1, beta, C, ldc, wait, put, as_stream(stream));
+}
+
 extern "C" void crp_cuda_spmm_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *recv_off)
 {
     if (plan != NULL) crp_panel_set_wait_map(plan, nslot, recv_off);
@@ -204,7 +238,6 @@ extern "C" void crp_cuda_spmm_exec_wait(
 )
 {
     if (plan == NULL) { fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: NULL plan\n"); abort(); }
-    cudaStream_t s = as_stream(stream);
     crp_spmm_wait wt, *wait = NULL;
     if (nwait > 0)
     {
@@ -212,16 +245,30 @@ extern "C" void crp_cuda_spmm_exec_wait(
         wt.timeout_ns = (long long) (timeout_s * 1e9);  wt.err = err;
         wait = &wt;
     }
-    if (plan->m == 0 || n <= 0) { wait_first(wait, s); return; }
+    spmm_exec_common(plan, n, elem_size, alpha, X0, ldx0, X1, ldx1, beta, C, ldc, wait, NULL, as_stream(stream));
+}
+
+static void spmm_exec_common(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha, const void *X0, const int ldx0, const void *X1, const int ldx1,
+    const double beta, void *C, const int ldc, const crp_spmm_wait *wait, const crp_spmm_put *put, cudaStream_t s
+)
+{
+    if (plan->m == 0 || n <= 0)
+    {
+        if (put != NULL && put->nflag > 0 && n > 0)
+            crp_cuda_put_rows_signal((size_t) elem_size, put->nrow, n, X0, ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, (void *) s);
+        wait_first(wait, s);
+        return;
+    }
     if (elem_size == 8)
     {
         spmm_dispatch<double, 2>(plan, plan->d_val, plan->rg.d_bval, n, (const double *) X0, (size_t) ldx0, (const double *) X1, (size_t) ldx1,
-                                 alpha, beta, (double *) C, (size_t) ldc, wait, s, "f64");
+                                 alpha, beta, (double *) C, (size_t) ldc, wait, put, 8, s, "f64");
     } else if (elem_size == 4) {
         cast_to_f32(plan->d_val, &plan->d_val32, (size_t) plan->nnz, s);
         if (plan->rg.d_bval != NULL) cast_to_f32(plan->rg.d_bval, &plan->rg.d_bval32, (size_t) plan->rg.nblk * (size_t) plan->rg.R, s);
         spmm_dispatch<float, 4>(plan, plan->d_val32, plan->rg.d_bval32, n, (const float *) X0, (size_t) ldx0, (const float *) X1, (size_t) ldx1,
-                                (float) alpha, (float) beta, (float *) C, (size_t) ldc, wait, s, "f32");
+                                (float) alpha, (float) beta, (float *) C, (size_t) ldc, wait, put, 4, s, "f32");
     } else {
         fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: elem_size must be 4 or 8\n");
         abort();

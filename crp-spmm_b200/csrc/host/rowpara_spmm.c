@@ -357,6 +357,28 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
         ASSERT_PRINTF(vcol[i] >= 0, "rp_spmm: column %d of the local A has no source row\n", rp->A_colidx[i]);
     }
     free(vid);
+    /* Rows whose virtual ids are not ascending (received rows have ids above the own ones whatever their global position)
+     * are put in ascending virtual order, values along: the kernels' row-group analysis wants sorted rows - without this the
+     * rows at a rank boundary fell out of the grouped form (465 "rest" rows on rank 1 of 2 on the pwtk-shaped matrix).  The
+     * public A_colidx / A_val keep the reference's order; only the device copy is permuted (a row's products are then added
+     * in a different order: within the 1e-12 contract, bit-identical between runs). */
+    double *vval = (double *) xmalloc(sizeof(double) * (size_t) (nnz > 0 ? nnz : 1));
+    memcpy(vval, rp->A_val, sizeof(double) * (size_t) nnz);
+    for (int i = 0; i < rp->A_nrow; i++)
+    {
+        const int b = rp->A_rowptr[i], e = rp->A_rowptr[i + 1];
+        int sorted = 1;
+        for (int p = b + 1; p < e; p++) if (vcol[p] < vcol[p - 1]) { sorted = 0; break; }
+        if (sorted) continue;
+        for (int p = b + 1; p < e; p++)         /* insertion sort: rows are short and nearly sorted (two sorted runs) */
+        {
+            const int c = vcol[p];
+            const double x = vval[p];
+            int q = p - 1;
+            while (q >= b && vcol[q] > c) { vcol[q + 1] = vcol[q]; vval[q + 1] = vval[q]; q--; }
+            vcol[q + 1] = c;  vval[q + 1] = x;
+        }
+    }
 
     /* transport: NCCL needs one device per rank; ranks that share a GPU stage the exchange through the host */
     int wsize = 1;
@@ -402,8 +424,8 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
         {
             for (int p = rp->A_rowptr[i]; p < rp->A_rowptr[i + 1]; p++)
             {
-                if (vcol[p] < d->nB) { ci_d[nd] = vcol[p]; v_d[nd++] = rp->A_val[p]; }
-                else                 { ci_o[no] = vcol[p]; v_o[no++] = rp->A_val[p]; }
+                if (vcol[p] < d->nB) { ci_d[nd] = vcol[p]; v_d[nd++] = vval[p]; }
+                else                 { ci_o[no] = vcol[p]; v_o[no++] = vval[p]; }
             }
             rp_d[i + 1] = nd;
             rp_o[i + 1] = no;
@@ -412,10 +434,11 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
         d->plan_off = (no > 0) ? crp_cuda_spmm_plan_create(m, d->nB + d->n_recv_rows, d->nB, rp_o, ci_o, v_o, n) : NULL;
         free(rp_d); free(rp_o); free(ci_d); free(ci_o); free(v_d); free(v_o);
     } else {
-        d->plan = crp_cuda_spmm_plan_create(rp->A_nrow, d->nB + d->n_recv_rows, d->nB, rp->A_rowptr, vcol, rp->A_val, n);
+        d->plan = crp_cuda_spmm_plan_create(rp->A_nrow, d->nB + d->n_recv_rows, d->nB, rp->A_rowptr, vcol, vval, n);
         d->plan_off = NULL;
     }
     free(vcol);
+    free(vval);
 
     if (d->n_send_rows > 0)
     {
@@ -687,17 +710,24 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     }
     const void *X1 = d->d_recvbuf;
     /* peer-memory transport without the overlap split: the SpMM kernel itself waits for the neighbours' flags */
-    int kwait = 0;
+    int kwait = 0, fused = 0;
     if (d->p2p && n > 0)
     {
         /* one launch: gather + NVLink stores into the peers' receive halves, then this rank's arrival flag on every neighbour */
         rp_p2p_tables(rp, d, elem_size);
         d->epoch++;
         const int half = (int) (d->epoch & 1u);
-        crp_cuda_put_rows_signal(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, (void *const *) d->d_dst_rows[half],
-                                 (unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, d->d_put_counter, cs);
-        CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0 || d->n_flag > 0, cs);
         X1 = (const char *) d->p2p_mem + CRP_P2P_HDR + (size_t) half * d->p2p_half_bytes;
+        fused = (!overlap && !d->p2p_hostsync) ? 1 : 0;
+        if (!fused)
+        {
+            /* one launch: gather + NVLink stores into the peers' receive halves, then this rank's arrival flag on every neighbour */
+            crp_cuda_put_rows_signal(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, (void *const *) d->d_dst_rows[half],
+                                     (unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, d->d_put_counter, cs);
+            CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0 || d->n_flag > 0, cs);
+        } else {
+            mark[CRP_EV_PACKED] = mark[CRP_EV_B_IN];        /* the SpMM kernel stores the rows itself */
+        }
         if (d->p2p_hostsync)
         {
             /* ranks sharing one GPU: no kernel may spin on another process' kernel - a host barrier after the puts have
@@ -739,10 +769,22 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     if (!overlap)
     {
         mark[CRP_EV_DIAG] = mark[CRP_EV_OFF0] = mark[CRP_EV_XCHG];
-        if (n > 0 && (m > 0 || kwait > 0))
+        if (fused)
+        {
+            /* ONE kernel: stores the rows the neighbours need into their receive halves, publishes the arrival flags, multiplies
+             * what needs only own rows, waits for a neighbour's flag right before the first tile that reads its rows */
+            crp_exchange xc;
+            memset(&xc, 0, sizeof(xc));
+            xc.n_send_rows = d->n_send_rows;  xc.send_ridx_d = d->d_sridxs;  xc.dst_rows_d = (void *const *) d->d_dst_rows[d->epoch & 1u];
+            xc.flag_ptrs_d = (unsigned int *const *) d->d_flag_ptrs;  xc.nflag = d->n_flag;  xc.done_counter_d = d->d_put_counter;
+            xc.flags_d = (const unsigned int *) d->p2p_mem;  xc.wait_idx_d = d->d_wait_idx;  xc.nwait = kwait;
+            xc.epoch = d->epoch;  xc.timeout_s = CRP_P2P_TIMEOUT_S;  xc.err = d->h_err;
+            crp_cuda_spmm_exec_exchange(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd, &xc, stream);
+        }
+        else if (n > 0 && (m > 0 || kwait > 0))
             crp_cuda_spmm_exec_wait(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd,
                                     (const unsigned int *) d->p2p_mem, d->d_wait_idx, kwait, d->epoch, CRP_P2P_TIMEOUT_S, d->h_err, stream);
-        CRP_MARK(CRP_EV_SPMM, n > 0 && (m > 0 || kwait > 0));
+        CRP_MARK(CRP_EV_SPMM, n > 0 && (m > 0 || kwait > 0 || fused));
     } else {
         if (m > 0 && n > 0) crp_cuda_spmm_exec(d->plan, n, elem_size, 1.0, Bd, (int) ldBd, X1, n, 0.0, Cd, (int) ldCd, stream);
         CRP_MARK(CRP_EV_DIAG, 1);

@@ -145,6 +145,32 @@ void crp_cuda_spmm_exec_wait(
     const unsigned int *flags_d, const int *wait_idx_d, const int nwait, const unsigned int epoch, const double timeout_s, int *err,
     void *stream
 );
+/* The whole exchange + product of one rp_spmm_exec in the peer-memory transport (successor of pack + MPI_Isend / Irecv /
+ * Waitall + mkl_sparse_d_mm at reference src/rowpara_spmm.c:232-408) as ONE fused kernel where the plan has the B-row-panel
+ * form: every thread block first stores its share of the rows the neighbours need (rows send_ridx_d of X0) straight into
+ * their receive buffers over NVLink, the last block to finish publishes this rank's arrival flag (value epoch) on every
+ * neighbour, and the product then runs as crp_cuda_spmm_exec_wait describes.  Plans without that form get the same effect
+ * from separate launches (crp_cuda_put_rows_signal, wait, SpMM). */
+typedef struct crp_exchange
+{
+    int       n_send_rows;                  /* rows this rank sends (0: it only publishes flags)            */
+    const int *send_ridx_d;                 /* device: their row numbers in X0                               */
+    void *const *dst_rows_d;                /* device: destination address of each row (peer memory)        */
+    unsigned int *const *flag_ptrs_d;       /* device: this rank's arrival flag on each neighbour            */
+    int       nflag;
+    unsigned int *done_counter_d;           /* device word, zero between launches                            */
+    const unsigned int *flags_d;            /* this rank's own flag words, one per rank                      */
+    const int *wait_idx_d;                  /* device: ranks whose flag is waited for                        */
+    int       nwait;
+    unsigned int epoch;
+    double    timeout_s;
+    int       *err;                         /* pinned host word set to 1 on timeout                          */
+} crp_exchange;
+void crp_cuda_spmm_exec_exchange(
+    crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
+    const void *X0, const int ldx0, const void *X1, const int ldx1, const double beta, void *C, const int ldc,
+    const crp_exchange *xc, void *stream
+);
 /* wait map: rows [recv_off[j], recv_off[j + 1]) of X1 are written by the neighbour of wait slot j (nslot <= 32) */
 void crp_cuda_spmm_set_wait_map(crp_spmm_plan *plan, const int nslot, const int *recv_off);
 /* name of the kernel variant the last crp_cuda_spmm_exec on this plan launched (static string) */

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--f32", action="store_true")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--rows", default="", help="a:b as fractions of m, e.g. 0.125:0.25 - time the kernel on a row slice (what one rank of several holds)")
     ap.add_argument("--ldb0", action="store_true", help="experiment: leading dimension 0, every B row aliases row 0 (all gathers hit L1)")
     a = ap.parse_args()
     L = capi.load()
@@ -33,6 +34,11 @@ def main():
     n = a.n or n
     dt = np.float32 if (a.f32 or dts == "f32") else np.float64
     m, k, rp, ci, v = gen.read_csr_bin(bench.matrix_path(a.workload))
+    if a.rows:
+        f0, f1 = (float(x) for x in a.rows.split(":"))
+        r0, r1 = int(f0 * m), int(f1 * m)
+        rp, ci, v = np.ascontiguousarray(rp[r0:r1 + 1] - rp[r0]), np.ascontiguousarray(ci[rp[r0]:rp[r1]]), np.ascontiguousarray(v[rp[r0]:rp[r1]])
+        m = r1 - r0
     nnz = int(rp[-1])
     es = np.dtype(dt).itemsize
     B = gen.fill_B(0, k, 0, n, dtype=dt)
