@@ -121,6 +121,20 @@ struct crp_spmm_put
     unsigned int *counter;      // device word, zero between launches
 };
 
+// Reuse profile of the B rows over the row sweep (built once at plan creation, O(nnz)): the sweep is cut into blocks of
+// CRP_REUSE_TILE rows; every use of a B row by a block other than the one that used it last is a "reuse" at distance
+// d = blocks in between.  With it the exec decides whether the product is made in several column passes so that the
+// window of B / C rows between a row's uses stays inside the 126 MB L2 (spmm_plan.cu: choose_passes).
+enum { CRP_REUSE_TILE = 32, CRP_REUSE_BUCKETS = 32 };
+struct crp_reuse
+{
+    long long ntile;                        // row blocks
+    long long first_uses;                   // B rows touched for the first time (compulsory reads)
+    long long reuses[CRP_REUSE_BUCKETS];    // bucket b: reuses at distance [2^b, 2^(b+1)) blocks
+    double    union_per_tile;               // distinct B rows a block touches, on average
+    double    new_per_tile;                 // first_uses / ntile
+};
+
 struct crp_spmm_plan
 {
     int       m, k;
@@ -143,7 +157,10 @@ struct crp_spmm_plan
     int       *h_rowptr;        // host copy of the row pointers (m + 1) for lazily built auxiliary structures
     crp_rowgroup_host *rg_host; // host copy of the row-group arrays (panel construction)
     crp_panel pn;
-    char      kernel_name[64];
+    crp_reuse reuse;
+    int       passes_forced;    // > 0: number of column passes set by crp_cuda_spmm_set_passes (experiments / tests)
+    int       last_passes;      // column passes of the last exec
+    char      kernel_name[80];
 };
 
 void crp_rowgroup_build(crp_spmm_plan *plan, const int *rowptr, const int *colidx, const double *val, std::vector<int> *rest_out);

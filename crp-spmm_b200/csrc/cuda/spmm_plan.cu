@@ -26,6 +26,101 @@ bool crp_launch_panel(
 template <typename T, int VEC>
 void crp_launch_rowgroup(const crp_rowgroup *rg, const T *bval, int nv, const T *X0, size_t ldx0, int x0_rows, const T *X1, size_t ldx1, T alpha, T beta, T *C, size_t ldc, cudaStream_t s);
 
+// Reuse-distance histogram of the B rows (crp_reuse in crp_cuda_internal.cuh).
+static void reuse_profile(crp_reuse *ru, const int m, const int k, const int *rowptr, const int *colidx)
+{
+    memset(ru, 0, sizeof(*ru));
+    if (m <= 0 || k <= 0 || rowptr[m] <= rowptr[0]) return;
+    std::vector<int> last((size_t) k, -1);
+    const long long ntile = ((long long) m + CRP_REUSE_TILE - 1) / CRP_REUSE_TILE;
+    long long uses = 0;
+    for (long long t = 0; t < ntile; t++)
+    {
+        const int r0 = (int) (t * CRP_REUSE_TILE), r1 = (int) ((t + 1) * CRP_REUSE_TILE < m ? (t + 1) * CRP_REUSE_TILE : m);
+        for (int q = rowptr[r0]; q < rowptr[r1]; q++)
+        {
+            const int c = colidx[q];
+            if (c < 0 || c >= k) continue;
+            const int l = last[(size_t) c];
+            if (l == (int) t) continue;
+            uses++;
+            if (l < 0) ru->first_uses++;
+            else
+            {
+                unsigned d = (unsigned) ((int) t - l);
+                int b = 0;
+                while (d > 1u) { d >>= 1; b++; }
+                ru->reuses[b]++;
+            }
+            last[(size_t) c] = (int) t;
+        }
+    }
+    ru->ntile = ntile;
+    ru->union_per_tile = (double) uses / (double) ntile;
+    ru->new_per_tile = (double) ru->first_uses / (double) ntile;
+}
+
+// Number of column passes for a product with n dense columns of es bytes.  Traffic model: a reuse at distance d blocks is an
+// L2 hit when the rows touched in between - the block's own union, (d - 1) blocks' new B rows, d blocks of C rows and of A -
+// fit into half of the L2; every pass re-reads A.  P is raised (1, 2, 4, 8) only when the modelled DRAM traffic drops by
+// more than 15 %.  A pass is at least 64 columns wide and a multiple of 64 columns (16-byte alignment for both types).
+static int model_passes(const crp_reuse *ru, const int m, const long long nnz, const int n, const int es, const double l2_bytes)
+{
+    if (ru->ntile == 0 || n < 128) return 1;
+    const double budget = 0.5 * l2_bytes;
+    const double a_bytes = (double) nnz * (4.0 + es) + 4.0 * m;
+    const double a_tile = a_bytes / (double) ru->ntile;
+    double best = 0.0;
+    int bestP = 1;
+    for (int P = 1; P <= 8; P *= 2)
+    {
+        const int ns = ((n + P - 1) / P + 63) / 64 * 64;
+        if (P > 1 && (ns < 64 || ns >= n)) break;
+        const double row = (double) ns * es;
+        double hits = 0.0;
+        for (int b = 0; b < CRP_REUSE_BUCKETS; b++)
+        {
+            if (ru->reuses[b] == 0) continue;
+            const double d = (double) (1ull << b) * 1.5;          // middle of the bucket
+            const double foot = (ru->union_per_tile + (d - 1.0) * ru->new_per_tile + d * CRP_REUSE_TILE) * row + d * a_tile;
+            if (foot <= budget) hits += (double) ru->reuses[b];
+        }
+        double all = (double) ru->first_uses;
+        for (int b = 0; b < CRP_REUSE_BUCKETS; b++) all += (double) ru->reuses[b];
+        const double traffic = (double) ((n + ns - 1) / ns) * a_bytes + (all - hits) * (double) n * es + (double) m * n * es;
+        if (P == 1 || traffic < 0.85 * best) { best = traffic; bestP = P; }
+    }
+    return bestP;
+}
+
+static int choose_passes(const crp_spmm_plan *p, const int n, const int es)
+{
+    if (p->passes_forced > 0) return p->passes_forced;
+    static int env = -1;
+    if (env < 0) { const char *e = getenv("CRP_SPMM_PASSES"); env = (e && e[0]) ? atoi(e) : 0; }
+    if (env > 0) return env;
+    static double l2_bytes = 0.0;
+    if (l2_bytes == 0.0)
+    {
+        int dev = 0, v = 0;
+        CRP_CUDA_CHECK(cudaGetDevice(&dev));
+        CRP_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev));
+        l2_bytes = (v > 0) ? (double) v : 64.0e6;
+    }
+    return model_passes(&p->reuse, p->m, p->nnz, n, es, l2_bytes);
+}
+
+// host-only view of the decision (no device needed): column passes the exec would use for this matrix, width and L2 size
+extern "C" int crp_cuda_spmm_model_passes(const int m, const int k, const int *rowptr_h, const int *colidx_h, const int n, const int elem_size, const double l2_bytes)
+{
+    crp_reuse ru;
+    reuse_profile(&ru, m, k, rowptr_h, colidx_h);
+    return model_passes(&ru, m, (m > 0) ? (long long) rowptr_h[m] - rowptr_h[0] : 0, n, elem_size, l2_bytes);
+}
+
+extern "C" void crp_cuda_spmm_set_passes(crp_spmm_plan *plan, const int passes) { if (plan != NULL) plan->passes_forced = passes; }
+extern "C" int crp_cuda_spmm_last_passes(const crp_spmm_plan *plan) { return plan ? plan->last_passes : 0; }
+
 extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, const int x0_rows, const int *rowptr_h, const int *colidx_h, const double *val_h, const int n_hint)
 {
     crp_spmm_plan *p = (crp_spmm_plan *) calloc(1, sizeof(crp_spmm_plan));
@@ -51,6 +146,7 @@ extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, co
         CRP_CUDA_CHECK(cudaMemcpy(p->d_colidx, colidx_h, sizeof(int) * (size_t) p->nnz, cudaMemcpyHostToDevice));
         CRP_CUDA_CHECK(cudaMemcpy(p->d_val, val_h, sizeof(double) * (size_t) p->nnz, cudaMemcpyHostToDevice));
     }
+    reuse_profile(&p->reuse, m, k, rowptr_h, colidx_h);
     std::vector<int> rest;
     crp_rowgroup_build(p, rowptr_h, colidx_h, val_h, &rest);
     if (p->rg.R > 1) crp_longrows_build(p, rowptr_h, rest.data(), (int) rest.size());
@@ -154,7 +250,7 @@ static void spmm_dispatch(
     }
     // the other kernels neither put nor wait themselves: separate launches first
     if (put != NULL && put->nflag > 0)
-        crp_cuda_put_rows_signal((size_t) n_elem_size, put->nrow, n, X0, (int) ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, (void *) s);
+        crp_cuda_put_rows_signal((size_t) n_elem_size, put->nrow, (int) (put->row_bytes / (size_t) n_elem_size), X0, (int) ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, (void *) s);
     wait_first(wait, s);
     // nnz-balanced kernel: forced, or chosen for matrices without row groups whose longest row is far above the average
     // (power-law graphs: one-row-per-warp leaves most warps idle behind the hubs)
@@ -260,18 +356,48 @@ static void spmm_exec_common(
         wait_first(wait, s);
         return;
     }
-    if (elem_size == 8)
+    if (elem_size != 4 && elem_size != 8)
     {
-        spmm_dispatch<double, 2>(plan, plan->d_val, plan->rg.d_bval, n, (const double *) X0, (size_t) ldx0, (const double *) X1, (size_t) ldx1,
-                                 alpha, beta, (double *) C, (size_t) ldc, wait, put, 8, s, "f64");
-    } else if (elem_size == 4) {
-        cast_to_f32(plan->d_val, &plan->d_val32, (size_t) plan->nnz, s);
-        if (plan->rg.d_bval != NULL) cast_to_f32(plan->rg.d_bval, &plan->rg.d_bval32, (size_t) plan->rg.nblk * (size_t) plan->rg.R, s);
-        spmm_dispatch<float, 4>(plan, plan->d_val32, plan->rg.d_bval32, n, (const float *) X0, (size_t) ldx0, (const float *) X1, (size_t) ldx1,
-                                (float) alpha, (float) beta, (float *) C, (size_t) ldc, wait, put, 4, s, "f32");
-    } else {
         fprintf(stderr, "[FATAL] crp_cuda_spmm_exec: elem_size must be 4 or 8\n");
         abort();
+    }
+    if (elem_size == 4)
+    {
+        cast_to_f32(plan->d_val, &plan->d_val32, (size_t) plan->nnz, s);
+        if (plan->rg.d_bval != NULL) cast_to_f32(plan->rg.d_bval, &plan->rg.d_bval32, (size_t) plan->rg.nblk * (size_t) plan->rg.R, s);
+    }
+    // Column passes sized for the L2 (choose_passes): the dense operands are cut into column blocks that are multiplied one
+    // after the other on the stream.  The first pass carries the exchange (put / wait); when it has finished every neighbour's
+    // rows have arrived (the kernels wait for all flags before they end), so the later passes need neither.
+    int P = choose_passes(plan, n, elem_size);
+    int ns = n;
+    if (P > 1)
+    {
+        ns = ((n + P - 1) / P + 63) / 64 * 64;
+        const uintptr_t al = (uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C | ((uintptr_t) ldx0 * elem_size) | ((uintptr_t) ldx1 * elem_size) | ((uintptr_t) ldc * elem_size);
+        if (ns >= n || (al & 15) != 0) { P = 1; ns = n; }
+    }
+    int npass = 0;
+    for (int c0 = 0; c0 < n; c0 += ns, npass++)
+    {
+        const int nn = (n - c0 < ns) ? n - c0 : ns;
+        const size_t off = (size_t) c0 * (size_t) elem_size;
+        const char *x0 = (const char *) X0 + off, *x1 = (X1 != NULL) ? (const char *) X1 + off : NULL;
+        char *c = (char *) C + off;
+        const crp_spmm_wait *w = (c0 == 0) ? wait : NULL;
+        const crp_spmm_put *pt = (c0 == 0) ? put : NULL;
+        if (elem_size == 8)
+            spmm_dispatch<double, 2>(plan, plan->d_val, plan->rg.d_bval, nn, (const double *) x0, (size_t) ldx0, (const double *) x1, (size_t) ldx1,
+                                     alpha, beta, (double *) c, (size_t) ldc, w, pt, 8, s, "f64");
+        else
+            spmm_dispatch<float, 4>(plan, plan->d_val32, plan->rg.d_bval32, nn, (const float *) x0, (size_t) ldx0, (const float *) x1, (size_t) ldx1,
+                                    (float) alpha, (float) beta, (float *) c, (size_t) ldc, w, pt, 4, s, "f32");
+    }
+    plan->last_passes = npass;
+    if (npass > 1)
+    {
+        const size_t len = strlen(plan->kernel_name);
+        snprintf(plan->kernel_name + len, sizeof(plan->kernel_name) - len, "_x%dpass", npass);
     }
 }
 

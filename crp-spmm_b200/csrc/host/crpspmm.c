@@ -21,6 +21,7 @@
 #include "utils.h"
 #include "spmat_part.h"
 #include "crpspmm.h"
+#include "crp_ext.h"
 #include "crp_internal.h"
 
 struct crp_composite
@@ -211,6 +212,10 @@ void crpspmm_engine_exec(
     const int me = e->rank_glb, nproc = e->np_glb, pn = e->np_col, pi = e->rank_row;
     const double t_start = get_wtime_sec();
     double t0, t1;
+    /* The three stages run on the engines' own streams and hand their results over through host synchronisation, so the
+     * composite always runs them with blocking semantics, whatever the caller set with crp_set_blocking(). */
+    const int caller_blocking = crp_opt_blocking();
+    crp_set_blocking(1);
 
     /* 1. A's values into the owned-rows layout; rebuild the 2-D engine only if they changed */
     t0 = get_wtime_sec();
@@ -263,6 +268,7 @@ void crpspmm_engine_exec(
     t1 = get_wtime_sec();
     e->t_exec_nr += t1 - t0;
     rp_spmm_p rp = e->p2d->rp_spmm;
+    rp_spmm_sync_stats(rp);                     /* fold this exec's CUDA-event times before reading the counters */
     e->t_a2a_B += (rp->t_a2a + rp->t_pack) - (c->prev_a2a + c->prev_pack);
     e->t_spmm  += rp->t_spmm - c->prev_spmm;
     c->prev_a2a = rp->t_a2a;  c->prev_pack = rp->t_pack;  c->prev_spmm = rp->t_spmm;
@@ -289,6 +295,7 @@ void crpspmm_engine_exec(
     t1 = get_wtime_sec();
     e->t_rd_C += t1 - t0;
 
+    crp_set_blocking(caller_blocking);
     e->t_exec += get_wtime_sec() - t_start;
     e->n_exec++;
 }

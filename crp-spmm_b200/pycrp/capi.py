@@ -207,6 +207,11 @@ def load():
     L.crp_cuda_spmm_last_kernel.argtypes = [vp]
     L.crp_cuda_spmm_last_kernel.restype = C.c_char_p
     L.crp_cuda_spmm_set_variant.argtypes = [vp, C.c_char_p]
+    L.crp_cuda_spmm_set_passes.argtypes = [vp, i]
+    L.crp_cuda_spmm_last_passes.argtypes = [vp]
+    L.crp_cuda_spmm_last_passes.restype = i
+    L.crp_cuda_spmm_model_passes.argtypes = [i, i, vp, vp, i, i, d]
+    L.crp_cuda_spmm_model_passes.restype = i
     L.crp_cuda_csr_spmm_host.argtypes = [i, i, i, d, i, vp, vp, vp, vp, i, d, vp, i]
     L.crp_cuda_spmm_plan_info.argtypes = [vp, vp]
     L.crp_cuda_measure_dfma_tflops.restype = d

@@ -177,6 +177,13 @@ void crp_cuda_spmm_set_wait_map(crp_spmm_plan *plan, const int nslot, const int 
 const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan);
 /* force a kernel variant for experiments: "auto", "rowsplit", "rowgroup", "panel", "mergepath" */
 void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name);
+/* Column passes: a product whose window of live B / C rows does not fit the L2 is made in several passes over column blocks
+ * of the dense operands (a multiple of 64 columns each), chosen per exec from the plan's reuse profile of the B rows.
+ * set_passes forces the number (0: automatic; CRP_SPMM_PASSES does the same for every plan), last_passes reports it. */
+void crp_cuda_spmm_set_passes(crp_spmm_plan *plan, const int passes);
+int crp_cuda_spmm_last_passes(const crp_spmm_plan *plan);
+/* host-only (no device needed): the number of passes the model picks for a CSR pattern, n columns of elem_size bytes, an L2 of l2_bytes */
+int crp_cuda_spmm_model_passes(const int m, const int k, const int *rowptr_h, const int *colidx_h, const int n, const int elem_size, const double l2_bytes);
 
 /* what the plan holds: out[0] group size R (1: none), [1] groups, [2] R x 1 blocks, [3] rows left to the row-split kernel,
  * [4] their nonzeros, [5] panel tiles, [6] panel chunks, [7] B rows staged per pass (sum of the tiles' unions), [8] 1 if all groups

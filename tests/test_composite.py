@@ -14,7 +14,6 @@ import oracle_lib as O
 from pycrp import gen
 from util import MINIMPIRUN, PKG, run_cmd
 
-UNVERIFIED = "written after the round-1 GPU budget was spent: the device path of the composite has not run on a GPU yet"
 
 
 def run(tmp_path, csr, n, nproc, *extra, plan_only=False, timeout=180):
@@ -51,7 +50,6 @@ def test_plan_and_A_redistribution(nproc, n, split, shape, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason=UNVERIFIED)
 @pytest.mark.parametrize("nproc,n,split,gather", [(1, 8, "even", False), (4, 16, "skew", False), (6, 24, "even", True)])
 def test_composite_exec(nproc, n, split, gather, tmp_path):
     mm, kk, rp, ci, v = gen.random_rect(300, 300, 7, seed=nproc, empty_rows=())
@@ -69,7 +67,6 @@ def test_composite_exec(nproc, n, split, gather, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason=UNVERIFIED)
 def test_deprecated_driver_runs_unchanged(tmp_path):
     exe = os.path.join(PKG, "bin", "test_crpspmm.exe")
     if not os.path.exists(exe):

@@ -72,7 +72,6 @@ def test_random_redist_host(seed, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent; the CUDA path is verified on the golden layouts (tests/test_redist.py)")
 @pytest.mark.parametrize("seed", [1, 4, 7])
 def test_random_redist_cuda(seed, tmp_path):
     run(tmp_path, seed, ("--cuda",))
