@@ -28,7 +28,10 @@ OBJS := $(addprefix $(OBJDIR)/host_,$(HOST_SRC:.c=.o)) $(addprefix $(OBJDIR)/com
 .PHONY: all lib drivers oracle clean
 all: lib
 
-lib: $(LIBDIR)/libminimpi.so $(BINDIR)/minimpirun $(LIBDIR)/libcrpspmm.so
+lib: $(LIBDIR)/libminimpi.so $(BINDIR)/minimpirun $(LIBDIR)/libcrpspmm.so $(LIBDIR)/libcrpingest.so
+
+$(LIBDIR)/libcrpingest.so: $(SRC)/ingest/mmio_fast.c | $(LIBDIR)
+	$(CC) -O3 -g -std=gnu11 -fPIC -fopenmp -Wall -shared -o $@ $<
 
 $(OBJDIR) $(LIBDIR) $(BINDIR):
 	mkdir -p $@
@@ -53,7 +56,9 @@ $(LIBDIR)/libcrpspmm.so: $(OBJS) $(LIBDIR)/libminimpi.so
 
 # ---- the reference's own drivers against this library (drop-in check) ----
 DRV_INC  := -I$(ROOT)/include -I$(MINIMPI) -I$(ROOT)/oracle/stubs -I$(REF)/examples
-DRV_HELP := mmio.c mmio_utils.c test_utils.c metis_mat_part.c
+# the drivers' matrix reader (mm_read_sparse_RPI + coo2csr of examples/mmio_utils.c) is replaced by the fast ingest library
+# (same signatures and results: csrc/ingest/mmio_fast.c, tests/test_ingest.py); everything else is the reference's source
+DRV_HELP := mmio.c test_utils.c metis_mat_part.c
 DRV_OBJS := $(addprefix $(OBJDIR)/drv_,$(DRV_HELP:.c=.o)) $(OBJDIR)/drv_mkl_standin.o $(OBJDIR)/drv_metis_stub.o
 DRV_CFLAGS := -O3 -march=x86-64-v3 -fopenmp -std=gnu11 -g -DUSE_MKL -Wno-unused-result
 
@@ -74,8 +79,8 @@ $(OBJDIR)/drv_mkl_standin.o: $(ROOT)/oracle/stubs/mkl_standin.c | $(OBJDIR)
 $(OBJDIR)/drv_metis_stub.o: $(ROOT)/oracle/stubs/metis_stub.c | $(OBJDIR)
 	$(CC) $(DRV_CFLAGS) $(DRV_INC) -c $< -o $@
 
-$(BINDIR)/%.exe: $(OBJDIR)/drv_%.o $(DRV_OBJS) $(LIBDIR)/libcrpspmm.so | $(BINDIR)
-	$(CC) -fopenmp -o $@ $< $(DRV_OBJS) -L$(LIBDIR) -lcrpspmm -lminimpi -lm -Wl,-rpath,'$$ORIGIN/../lib'
+$(BINDIR)/%.exe: $(OBJDIR)/drv_%.o $(DRV_OBJS) $(LIBDIR)/libcrpspmm.so $(LIBDIR)/libcrpingest.so | $(BINDIR)
+	$(CC) -fopenmp -o $@ $< $(DRV_OBJS) -L$(LIBDIR) -lcrpspmm -lcrpingest -lminimpi -lm -Wl,-rpath,'$$ORIGIN/../lib'
 
 oracle:
 	$(MAKE) -C $(ROOT)/oracle all

@@ -374,7 +374,7 @@ template <typename V>
 __global__ void __launch_bounds__(256) put_rows_signal_kernel(
     const char *__restrict__ src, const size_t src_pitch, const int *__restrict__ ridx, char *const *__restrict__ dst_rows,
     const uint32_t nrow, const uint32_t row_bytes, unsigned int *const *__restrict__ flag_ptrs, const int nflag, const unsigned int epoch,
-    unsigned int *__restrict__ done_counter
+    unsigned int *__restrict__ done_counter, const size_t dst_off
 )
 {
     const uint32_t vpr = row_bytes / (uint32_t) sizeof(V);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) put_rows_signal_kernel(
     {
         const uint32_t r = (uint32_t) (t / vpr), v = (uint32_t) (t - (size_t) r * vpr);
         const V val = *reinterpret_cast<const V *>(src + (size_t) ridx[r] * src_pitch + (size_t) v * sizeof(V));
-        *reinterpret_cast<V *>(dst_rows[r] + (size_t) v * sizeof(V)) = val;
+        *reinterpret_cast<V *>(dst_rows[r] + dst_off + (size_t) v * sizeof(V)) = val;
     }
     __threadfence_system();
     __syncthreads();
@@ -399,16 +399,16 @@ __global__ void __launch_bounds__(256) put_rows_signal_kernel(
 
 extern "C" void crp_cuda_put_rows_signal(
     size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, const int *ridx_d, void *const *dst_rows_d,
-    unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, unsigned int *done_counter_d, void *stream
+    unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, unsigned int *done_counter_d, const size_t dst_off_bytes, void *stream
 )
 {
     if (nflag <= 0 && (nrow <= 0 || ncol <= 0)) return;
     const size_t row_bytes = dt_size * (size_t) (ncol > 0 ? ncol : 0), pitch = dt_size * (size_t) lds;
     const uint32_t rows = (nrow > 0 && ncol > 0) ? (uint32_t) nrow : 0u;
     const int grid = rows ? copy_grid((size_t) rows * (row_bytes / 4)) : 1;
-#define CRP_PUT(V) put_rows_signal_kernel<V><<<grid, 256, 0, as_stream(stream)>>>((const char *) src, pitch, ridx_d, (char *const *) dst_rows_d, rows, (uint32_t) row_bytes, flag_ptrs_d, nflag, epoch, done_counter_d)
-    if (((uintptr_t) src & 15) == 0 && pitch % 16 == 0 && row_bytes % 16 == 0) CRP_PUT(uint4);
-    else if (((uintptr_t) src & 7) == 0 && pitch % 8 == 0 && row_bytes % 8 == 0) CRP_PUT(uint2);
+#define CRP_PUT(V) put_rows_signal_kernel<V><<<grid, 256, 0, as_stream(stream)>>>((const char *) src, pitch, ridx_d, (char *const *) dst_rows_d, rows, (uint32_t) row_bytes, flag_ptrs_d, nflag, epoch, done_counter_d, dst_off_bytes)
+    if (((uintptr_t) src & 15) == 0 && pitch % 16 == 0 && row_bytes % 16 == 0 && dst_off_bytes % 16 == 0) CRP_PUT(uint4);
+    else if (((uintptr_t) src & 7) == 0 && pitch % 8 == 0 && row_bytes % 8 == 0 && dst_off_bytes % 8 == 0) CRP_PUT(uint2);
     else CRP_PUT(uint32_t);
 #undef CRP_PUT
     CRP_LAUNCH_CHECK();

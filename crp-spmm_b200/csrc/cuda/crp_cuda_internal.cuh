@@ -86,6 +86,7 @@ struct crp_panel
 {
     void      *host;            // crp_panel_host (structure kept for the lazily built fp32 records and the wait map)
     int       K, CR, EMAX, R;
+    int       clustered;        // tiles formed by column overlap (1) or K consecutive groups (0)
     int       ntiles, nchunks;
     long long union_rows;       // B rows staged per pass over the matrix
     int       *d_tile_chunk_ptr;
@@ -119,6 +120,7 @@ struct crp_spmm_put
     int       nflag;
     unsigned  epoch;
     unsigned int *counter;      // device word, zero between launches
+    size_t    dst_off;          // bytes added to every destination (column block of wider rows)
 };
 
 // Reuse profile of the B rows over the row sweep (built once at plan creation, O(nnz)): the sweep is cut into blocks of

@@ -190,6 +190,7 @@ struct panel_args
     unsigned int *const *put_flag_ptrs; // this rank's flag on each neighbour
     int put_nflag;
     unsigned int *put_counter;          // blocks that have finished their share (reset by the last one)
+    size_t put_dst_off;                 // bytes added to every destination
     int nwait;
     int wait_all_first;                 // no wait map for this neighbour list: wait for everybody before the first chunk
     unsigned epoch;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
         {
             const unsigned r = (unsigned) (t / vpr), v = (unsigned) (t - (size_t) r * vpr);
             const uint4 val = *reinterpret_cast<const uint4 *>(a.X0 + (size_t) a.put_ridx[r] * a.ldx0 + (size_t) v * 16);
-            *reinterpret_cast<uint4 *>(a.put_dst_rows[r] + (size_t) v * 16) = val;
+            *reinterpret_cast<uint4 *>(a.put_dst_rows[r] + a.put_dst_off + (size_t) v * 16) = val;
         }
         __threadfence_system();
     }
@@ -649,6 +650,23 @@ void crp_panel_build(crp_spmm_plan *plan)
     if (EMAX < K) EMAX = K;
     crp_panel_host *ph = new crp_panel_host();
     crp_panel_build_structure(*rg, K, CR, EMAX, ph);
+    // Tiles as patches of K groups with the largest column overlap (crp_panel_cluster_tiles) instead of K consecutive groups:
+    // kept only where the panels shrink by more than a third.  Measured on B200 (profiles/r02_kbench_cluster.log): the 27-point
+    // stencil (staged rows -51 %) gains 13 % (12.1 -> 10.5 ms), the headline FEM matrix (-17 %) LOSES 7 % (0.320 -> 0.344 ms) -
+    // its consecutive-node tiles give every consumer warp the same number of entries in every chunk, the 2-D patches do not,
+    // and the chunks are consumed in lockstep.  CRP_PANEL_CLUSTER = 0 / 1 forces the choice.
+    const int want_cluster = panel_env_int("CRP_PANEL_CLUSTER", -1);
+    if (want_cluster != 0)
+    {
+        int ncols = 0;
+        for (size_t b = 0; b < rg->b_col.size(); b++) if (rg->b_col[b] >= ncols) ncols = rg->b_col[b] + 1;
+        std::vector<int> order;
+        crp_panel_cluster_tiles(*rg, K, ncols, &order);
+        crp_panel_host *pc = new crp_panel_host();
+        crp_panel_build_structure(*rg, K, CR, EMAX, pc, &order);
+        if (want_cluster == 1 || 3 * pc->ucol.size() < 2 * ph->ucol.size()) { delete ph; ph = pc; pn->clustered = 1; }
+        else delete pc;
+    }
     pn->host = ph;
     pn->K = K;  pn->CR = CR;  pn->EMAX = EMAX;  pn->R = rg->R;
     pn->ntiles = ph->ntiles;  pn->nchunks = ph->nchunks();  pn->union_rows = (long long) ph->ucol.size();
@@ -794,7 +812,7 @@ bool crp_launch_panel(
     *rest_done = false;
     crp_panel *pn = &plan->pn;
     if (pn->host == NULL || pn->ntiles == 0) return false;
-    if (put != NULL && (put->row_bytes % 16 != 0 || ((uintptr_t) X0 & 15) != 0)) return false;       // the fused put moves 16-byte units
+    if (put != NULL && (put->row_bytes % 16 != 0 || put->dst_off % 16 != 0 || ((uintptr_t) X0 & 15) != 0)) return false;       // the fused put moves 16-byte units
     const size_t es = sizeof(T);
     if (n < 64 || (n * es) % 16 != 0 || (ldx0 * es) % 16 != 0 || (X1 != NULL && (ldx1 * es) % 16 != 0) || (ldc * es) % 16 != 0) return false;
     if ((((uintptr_t) X0 | (uintptr_t) X1 | (uintptr_t) C) & 15) != 0) return false;
@@ -833,7 +851,7 @@ bool crp_launch_panel(
     {
         a.put_nrow = put->nrow;  a.put_row_bytes = (unsigned) put->row_bytes;  a.put_ridx = put->ridx;
         a.put_dst_rows = (char *const *) put->dst_rows;  a.put_flag_ptrs = put->flag_ptrs;  a.put_nflag = put->nflag;
-        a.put_counter = put->counter;  a.epoch = put->epoch;
+        a.put_counter = put->counter;  a.epoch = put->epoch;  a.put_dst_off = put->dst_off;
     }
     switch (pn->R)
     {

@@ -93,12 +93,23 @@ static int model_passes(const crp_reuse *ru, const int m, const long long nnz, c
     return bestP;
 }
 
+static bool passes_env_is_model()
+{
+    const char *e = getenv("CRP_SPMM_PASSES");
+    return e != NULL && strcmp(e, "model") == 0;
+}
+
+// Column passes are OPT-IN: measured on B200 (profiles/r02_kbench_stencil_passes.log) one pass is the fastest on every BASELINE
+// shape - the 126 MB L2 and the kernels' access order already keep the re-read B rows close, and every extra pass re-reads A
+// and the panel's meta records.  CRP_SPMM_PASSES=<count> / crp_cuda_spmm_set_passes force a count, CRP_SPMM_PASSES=model
+// (set when the plan is created) lets the traffic model above decide, for GPUs with a smaller L2.
 static int choose_passes(const crp_spmm_plan *p, const int n, const int es)
 {
     if (p->passes_forced > 0) return p->passes_forced;
-    static int env = -1;
-    if (env < 0) { const char *e = getenv("CRP_SPMM_PASSES"); env = (e && e[0]) ? atoi(e) : 0; }
+    const char *e = getenv("CRP_SPMM_PASSES");
+    const int env = (e && e[0]) ? atoi(e) : 0;
     if (env > 0) return env;
+    if (!passes_env_is_model() || p->reuse.ntile == 0) return 1;
     static double l2_bytes = 0.0;
     if (l2_bytes == 0.0)
     {
@@ -146,7 +157,7 @@ extern "C" crp_spmm_plan *crp_cuda_spmm_plan_create(const int m, const int k, co
         CRP_CUDA_CHECK(cudaMemcpy(p->d_colidx, colidx_h, sizeof(int) * (size_t) p->nnz, cudaMemcpyHostToDevice));
         CRP_CUDA_CHECK(cudaMemcpy(p->d_val, val_h, sizeof(double) * (size_t) p->nnz, cudaMemcpyHostToDevice));
     }
-    reuse_profile(&p->reuse, m, k, rowptr_h, colidx_h);
+    if (passes_env_is_model()) reuse_profile(&p->reuse, m, k, rowptr_h, colidx_h);
     std::vector<int> rest;
     crp_rowgroup_build(p, rowptr_h, colidx_h, val_h, &rest);
     if (p->rg.R > 1) crp_longrows_build(p, rowptr_h, rest.data(), (int) rest.size());
@@ -250,7 +261,7 @@ static void spmm_dispatch(
     }
     // the other kernels neither put nor wait themselves: separate launches first
     if (put != NULL && put->nflag > 0)
-        crp_cuda_put_rows_signal((size_t) n_elem_size, put->nrow, (int) (put->row_bytes / (size_t) n_elem_size), X0, (int) ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, (void *) s);
+        crp_cuda_put_rows_signal((size_t) n_elem_size, put->nrow, (int) (put->row_bytes / (size_t) n_elem_size), X0, (int) ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, put->dst_off, (void *) s);
     wait_first(wait, s);
     // nnz-balanced kernel: forced, or chosen for matrices without row groups whose longest row is far above the average
     // (power-law graphs: one-row-per-warp leaves most warps idle behind the hubs)
@@ -314,7 +325,7 @@ extern "C" void crp_cuda_spmm_exec_exchange(
     if (xc != NULL && xc->nflag > 0)
     {
         pt.nrow = xc->n_send_rows;  pt.row_bytes = (size_t) elem_size * (size_t) n;  pt.ridx = xc->send_ridx_d;  pt.dst_rows = xc->dst_rows_d;
-        pt.flag_ptrs = xc->flag_ptrs_d;  pt.nflag = xc->nflag;  pt.epoch = xc->epoch;  pt.counter = xc->done_counter_d;
+        pt.flag_ptrs = xc->flag_ptrs_d;  pt.nflag = xc->nflag;  pt.epoch = xc->epoch;  pt.counter = xc->done_counter_d;  pt.dst_off = xc->dst_off_bytes;
         put = &pt;
     }
     spmm_exec_common(plan, n, elem_size, alpha, X0, ldx0, X1, ldx1, beta, C, ldc, wait, put, as_stream(stream));
@@ -352,7 +363,7 @@ static void spmm_exec_common(
     if (plan->m == 0 || n <= 0)
     {
         if (put != NULL && put->nflag > 0 && n > 0)
-            crp_cuda_put_rows_signal((size_t) elem_size, put->nrow, n, X0, ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, (void *) s);
+            crp_cuda_put_rows_signal((size_t) elem_size, put->nrow, n, X0, ldx0, put->ridx, put->dst_rows, put->flag_ptrs, put->nflag, put->epoch, put->counter, put->dst_off, (void *) s);
         wait_first(wait, s);
         return;
     }

@@ -45,6 +45,7 @@ void  crp_nccl_shutdown(void);
 int  *crp_comm_ranks_in_parent(MPI_Comm sub, MPI_Comm parent);
 
 /* ---- device-side state of a row-parallel engine (rowpara_spmm.c) ---- */
+enum { CRP_E2E_MAX_PANELS = 16 };
 enum { CRP_EV_START = 0, CRP_EV_B_IN, CRP_EV_PACKED, CRP_EV_XCHG, CRP_EV_DIAG, CRP_EV_OFF0, CRP_EV_SPMM, CRP_EV_END, CRP_RP_NEV };
 enum { CRP_RP_RING = 8 };
 
@@ -95,6 +96,10 @@ struct crp_rp_dev
     unsigned int epoch;
     crp_nccl_comm *nc;          /* NCCL communicator used for the B-row exchange                     */
     int     *peer_nc_rank;      /* nproc: rank of each member of rp->comm inside nc                  */
+    /* host B / C: column panels pipelined over three streams (H2D | exchange + product | D2H)       */
+    void    *stream_in, *stream_out;
+    void    *ev_in[CRP_E2E_MAX_PANELS], *ev_out[CRP_E2E_MAX_PANELS];
+    int     e2e_panels;         /* panels of the last pipelined exec (0: the last exec was not pipelined) */
 };
 
 /* rp_spmm_init with an explicit NCCL parent: the exchange runs on the NCCL

@@ -209,7 +209,7 @@ void crpspmm_engine_exec(
         fflush(stderr);
         abort();
     }
-    const int me = e->rank_glb, nproc = e->np_glb, pn = e->np_col, pi = e->rank_row;
+    const int pn = e->np_col, pi = e->rank_row;
     const double t_start = get_wtime_sec();
     double t0, t1;
     /* The three stages run on the engines' own streams and hand their results over through host synchronisation, so the
@@ -222,9 +222,9 @@ void crpspmm_engine_exec(
     crpspmm_engine_redist_A_values(e, src_A_val);
     t1 = get_wtime_sec();
     e->t_rd_A += t1 - t0;
-    size_t moved = 0;
-    for (int p = 0; p < nproc; p++) if (p != me) moved += (size_t) c->r_cnt[p];
-    e->nelem_A_rd = moved;
+    /* the counters follow the reference's definitions (deprecated/src/crpspmm.c:449-456, 587-596): what each rank HOLDS after
+     * a phase, its own share included - not what crossed a link */
+    e->nelem_A_rd = (size_t) e->loc_A_nnz;
     int rebuild = !c->have_engine || memcmp(c->val_cache, e->loc_A_val, sizeof(double) * (size_t) e->loc_A_nnz) != 0;
     int any = 0;
     MPI_Allreduce(&rebuild, &any, 1, MPI_INT, MPI_MAX, e->comm_glb);        /* para2d_spmm_init is collective */
@@ -239,7 +239,7 @@ void crpspmm_engine_exec(
         e->t_agv_A += e->p2d->t_ag_A;
         const int *G = c->glb_rowptr;
         const size_t panel = (size_t) (G[c->A0_rowptr[(pi + 1) * pn]] - G[c->A0_rowptr[pi * pn]]);
-        e->nelem_A_agv = panel - (size_t) e->loc_A_nnz;
+        e->nelem_A_agv = (pn > 1) ? panel : 0;
     }
 
     /* 2. B: caller's block -> the grid's block, on the device */
@@ -258,9 +258,7 @@ void crpspmm_engine_exec(
     mat_redist_engine_exec(e->rd_B, Bsrc, ldBsrc, c->dB_loc, e->loc_B_ncol);
     t1 = get_wtime_sec();
     e->t_rd_B += t1 - t0;
-    size_t self = 0;
-    for (int i = 0; i < e->rd_B->n_proc_recv; i++) if (e->rd_B->recv_ranks[i] == me) self = (size_t) e->rd_B->recv_sizes[i];
-    e->nelem_B_rd = (size_t) e->rd_B->recv_cnt - self;
+    e->nelem_B_rd = (size_t) e->rd_B->recv_cnt;
 
     /* 3. replicate B + local SpMM on device-resident blocks */
     t0 = get_wtime_sec();
@@ -272,8 +270,9 @@ void crpspmm_engine_exec(
     e->t_a2a_B += (rp->t_a2a + rp->t_pack) - (c->prev_a2a + c->prev_pack);
     e->t_spmm  += rp->t_spmm - c->prev_spmm;
     c->prev_a2a = rp->t_a2a;  c->prev_pack = rp->t_pack;  c->prev_spmm = rp->t_spmm;
-    e->nelem_B_a2av = rp->rB_recv_size * (size_t) rp->glb_n;
-    e->nelem_B_a2av_min = e->nelem_B_a2av;      /* only the needed rows travel (the reference's fine-grained mode) */
+    /* only the needed rows travel (the reference's A2A_B_FINEGRAIN=1 mode): own rows + received rows, times the local width */
+    e->nelem_B_a2av_min = ((size_t) rp->rB_self_nrow + rp->rB_recv_size) * (size_t) rp->glb_n;
+    e->nelem_B_a2av = (e->np_row > 1) ? e->nelem_B_a2av_min : 0;
 
     /* 4. C: the grid's block -> caller's block */
     t0 = get_wtime_sec();

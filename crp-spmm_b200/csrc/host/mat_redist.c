@@ -35,6 +35,8 @@ struct crp_redist_dev
     int  staged;
     void *stream;
     crp_nccl_comm *nc;
+    void *own_stage_h;          /* pinned staging buffer of the engine itself: the staged route with a caller who attached */
+                                /* no host buffer (DEV_TYPE_CUDA_MPI_DIRECT asks for a device buffer only)                */
 };
 
 static int is_cuda_type(dev_type_t t) { return (t == DEV_TYPE_CUDA) || (t == DEV_TYPE_CUDA_MPI_DIRECT); }
@@ -196,6 +198,7 @@ void mat_redist_engine_free(mat_redist_engine_p *engine_)
         crp_cuda_free_dev(d->d_pack);
         crp_cuda_free_dev(d->d_unpack);
         crp_cuda_free_dev(d->d_self);
+        if (d->own_stage_h) crp_cuda_free_host(d->own_stage_h);
         crp_cuda_stream_destroy(d->stream);
         free(d);
     }
@@ -303,6 +306,12 @@ static void redist_exec_cuda(mat_redist_engine_p eng, const void *src_blk, const
         }
     } else {
         /* ranks share a GPU: host-staged exchange, the reference's DEV_TYPE_CUDA route */
+        if (eng->sendbuf_h == NULL && (eng->send_cnt > 0 || eng->recv_cnt > 0))
+        {
+            crp_cuda_malloc_host(&d->own_stage_h, es * ((size_t) eng->send_cnt + (size_t) eng->recv_cnt));
+            eng->sendbuf_h = d->own_stage_h;
+            eng->recvbuf_h = (char *) d->own_stage_h + es * (size_t) eng->send_cnt;
+        }
         const double t0 = get_wtime_sec();
         if (eng->send_cnt > 0) crp_cuda_memcpy_async(eng->sendbuf_d, eng->sendbuf_h, es * (size_t) eng->send_cnt, stream);
         crp_cuda_stream_sync(stream);

@@ -468,6 +468,7 @@ static void rp_free_device_state(rp_spmm_p rp)
     if (d == NULL) return;
     crp_cuda_stream_sync(d->stream);
     crp_cuda_stream_sync(d->stream2);
+    if (d->stream_in != NULL) { crp_cuda_stream_sync(d->stream_in); crp_cuda_stream_sync(d->stream_out); }
     rp_p2p_teardown(rp, d);
     crp_cuda_spmm_plan_destroy(d->plan);
     crp_cuda_spmm_plan_destroy(d->plan_off);
@@ -483,6 +484,12 @@ static void rp_free_device_state(rp_spmm_p rp)
         for (int i = 0; i < CRP_RP_NEV; i++) crp_cuda_event_destroy(d->ev[k][i]);
     crp_cuda_stream_destroy(d->stream);
     crp_cuda_stream_destroy(d->stream2);
+    if (d->stream_in != NULL)
+    {
+        for (int j = 0; j < CRP_E2E_MAX_PANELS; j++) { crp_cuda_event_destroy(d->ev_in[j]); crp_cuda_event_destroy(d->ev_out[j]); }
+        crp_cuda_stream_destroy(d->stream_in);
+        crp_cuda_stream_destroy(d->stream_out);
+    }
     free(d->send_rows);
     free(d->recv_rows);
     free(d->peer_nc_rank);
@@ -639,6 +646,38 @@ static void rp_exchange(rp_spmm_p rp, struct crp_rp_dev *d, const size_t row_byt
     if (d->n_recv_rows > 0) crp_cuda_memcpy_async(d->h_recvbuf, d->d_recvbuf, row_bytes * (size_t) d->n_recv_rows, stream);
 }
 
+
+/*
+ * Host-resident B and C (the reference's own calling convention, src/rowpara_spmm.c:188-227): column j of C depends on column j
+ * of B only, so the call is cut into column panels that flow through three streams -
+ *     stream_in :  H2D panel 0 | H2D panel 1 | H2D panel 2 | ...
+ *     stream    :              | exchange + product 0 | exchange + product 1 | ...
+ *     stream_out:                                     | D2H panel 0 | D2H panel 1 | ...
+ * - and the two PCIe directions work at the same time instead of one after the other (round 1: 8.1 + 0.4 + 8.1 ms serial).
+ * Every panel is a complete exchange round of the peer-memory transport (own epoch, alternating receive halves), restricted
+ * to the panel's columns of the full-width receive buffer.  Returns the number of panels (0: not applicable - the caller
+ * runs the serial path).  CRP_SPMM_E2E_PANELS sets the count (default 4, 1 = off).
+ */
+static int rp_e2e_panel_count(rp_spmm_p rp, struct crp_rp_dev *d, const int BC_layout, const int B_on_dev, const int C_on_dev, const int elem_size)
+{
+    static int want = -1;
+    if (want < 0) GET_ENV_INT_VAR(want, "CRP_SPMM_E2E_PANELS", "e2e_panels", 4, 1, CRP_E2E_MAX_PANELS, 0);
+    const int n = rp->glb_n;
+    int P = want;
+    while (P > 1 && n / P < 32) P--;
+    /* a panel starts on a 16-byte boundary in both types: multiples of 4 columns */
+    int ok = (P > 1) && BC_layout == 0 && !B_on_dev && !C_on_dev && rp->A_nrow > 0 && d->nB > 0 && (n % 4 == 0);
+    if (rp->nproc > 1)
+    {
+        /* every rank must cut the call the same way (each panel is an exchange round); only the fused peer-memory route */
+        ok = ok && d->p2p && !d->overlap && !d->p2p_hostsync && ((size_t) elem_size * (size_t) n) % 16 == 0;
+        int all = 0;
+        MPI_Allreduce(&ok, &all, 1, MPI_INT, MPI_MIN, rp->comm);
+        ok = all;
+    }
+    return ok ? P : 0;
+}
+
 void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const int ldB, void *C, const int ldC, const int elem_size)
 {
     if (rp == NULL) return;
@@ -660,10 +699,71 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     const size_t es = (size_t) elem_size;
     const size_t row_bytes = es * (size_t) n;
     void *stream = crp_opt_stream() ? crp_opt_stream() : d->stream;
+    int overlap = d->overlap;
     const int B_on_dev = (nB > 0 && n > 0) ? crp_cuda_ptr_is_device(B) : 1;
     const int C_on_dev = (m > 0 && n > 0) ? crp_cuda_ptr_is_device(C) : 1;
 
     CRP_MARK(CRP_EV_START, 1);
+
+    const int npanel = rp_e2e_panel_count(rp, d, BC_layout, B_on_dev, C_on_dev, elem_size);
+    d->e2e_panels = npanel;
+    if (npanel > 1)
+    {
+        if (d->stream_in == NULL)
+        {
+            d->stream_in = crp_cuda_stream_create();
+            d->stream_out = crp_cuda_stream_create();
+            for (int j = 0; j < CRP_E2E_MAX_PANELS; j++) { d->ev_in[j] = crp_cuda_event_create(); d->ev_out[j] = crp_cuda_event_create(); }
+        }
+        crp_pin_host_range(B, es * ((size_t) (nB - 1) * (size_t) ldB + (size_t) n));
+        crp_pin_host_range(C, es * ((size_t) (m - 1) * (size_t) ldC + (size_t) n));
+        grow_dev(&d->d_Bwork, &d->Bwork_bytes, row_bytes * (size_t) nB);
+        grow_dev(&d->d_Cwork, &d->Cwork_bytes, row_bytes * (size_t) m);
+        if (d->p2p) rp_p2p_tables(rp, d, elem_size);
+        const int pw = ((n + npanel - 1) / npanel + 3) / 4 * 4;         /* panel width in columns */
+        crp_cuda_stream_wait_event(d->stream_in, mark[CRP_EV_START]);
+        int np = 0;
+        for (int c0 = 0; c0 < n; c0 += pw, np++)
+        {
+            const int w = (n - c0 < pw) ? n - c0 : pw;
+            const size_t off = es * (size_t) c0;
+            crp_cuda_memcpy2d_async((const char *) B + off, es * (size_t) ldB, (char *) d->d_Bwork + off, row_bytes, es * (size_t) w, (size_t) nB, d->stream_in);
+            crp_cuda_event_record(d->ev_in[np], d->stream_in);
+        }
+        np = 0;
+        for (int c0 = 0; c0 < n; c0 += pw, np++)
+        {
+            const int w = (n - c0 < pw) ? n - c0 : pw;
+            const size_t off = es * (size_t) c0;
+            crp_cuda_stream_wait_event(stream, d->ev_in[np]);
+            if (np == 0) { crp_cuda_event_record(ev[CRP_EV_B_IN], stream); mark[CRP_EV_B_IN] = ev[CRP_EV_B_IN]; }
+            if (d->p2p)
+            {
+                d->epoch++;
+                const int half = (int) (d->epoch & 1u);
+                const char *X1 = (const char *) d->p2p_mem + CRP_P2P_HDR + (size_t) half * d->p2p_half_bytes + off;
+                crp_exchange xc;
+                memset(&xc, 0, sizeof(xc));
+                xc.n_send_rows = d->n_send_rows;  xc.send_ridx_d = d->d_sridxs;  xc.dst_rows_d = (void *const *) d->d_dst_rows[half];
+                xc.flag_ptrs_d = (unsigned int *const *) d->d_flag_ptrs;  xc.nflag = d->n_flag;  xc.done_counter_d = d->d_put_counter;
+                xc.flags_d = (const unsigned int *) d->p2p_mem;  xc.wait_idx_d = d->d_wait_idx;  xc.nwait = d->n_wait;
+                xc.epoch = d->epoch;  xc.timeout_s = CRP_P2P_TIMEOUT_S;  xc.err = d->h_err;  xc.dst_off_bytes = off;
+                crp_cuda_spmm_exec_exchange(d->plan, w, elem_size, 1.0, (const char *) d->d_Bwork + off, n, X1, n, 0.0, (char *) d->d_Cwork + off, n, &xc, stream);
+            }
+            else crp_cuda_spmm_exec(d->plan, w, elem_size, 1.0, (const char *) d->d_Bwork + off, n, NULL, 0, 0.0, (char *) d->d_Cwork + off, n, stream);
+            crp_cuda_event_record(d->ev_out[np], stream);
+            crp_cuda_stream_wait_event(d->stream_out, d->ev_out[np]);
+            crp_cuda_memcpy2d_async((const char *) d->d_Cwork + off, row_bytes, (char *) C + off, es * (size_t) ldC, es * (size_t) w, (size_t) m, d->stream_out);
+        }
+        /* phase marks of a pipelined exec: H2D = start .. first panel on the device, SpMM = that .. last product done (the
+         * remaining H2D hides under it), D2H = the exposed tail after the last product */
+        mark[CRP_EV_PACKED] = mark[CRP_EV_XCHG] = mark[CRP_EV_DIAG] = mark[CRP_EV_OFF0] = mark[CRP_EV_B_IN];
+        crp_cuda_event_record(ev[CRP_EV_SPMM], stream);   mark[CRP_EV_SPMM] = ev[CRP_EV_SPMM];
+        crp_cuda_event_record(ev[CRP_EV_END], d->stream_out);  mark[CRP_EV_END] = ev[CRP_EV_END];
+        crp_cuda_stream_wait_event(stream, mark[CRP_EV_END]);          /* later work on the engine's stream follows the last D2H */
+        overlap = 0;
+        goto exec_enqueued;
+    }
 
     /* ---- B as a row-major device matrix Bd (leading dimension ldBd) ---- */
     const void *Bd = B;
@@ -701,7 +801,6 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
     CRP_MARK(CRP_EV_B_IN, Bd != B);
 
     /* ---- pack the rows other ranks need, exchange: on the communication stream in overlap mode ---- */
-    const int overlap = d->overlap;
     void *cs = overlap ? d->stream2 : stream;
     if (overlap)
     {
@@ -723,7 +822,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         {
             /* one launch: gather + NVLink stores into the peers' receive halves, then this rank's arrival flag on every neighbour */
             crp_cuda_put_rows_signal(es, d->n_send_rows, n, Bd, (int) ldBd, d->d_sridxs, (void *const *) d->d_dst_rows[half],
-                                     (unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, d->d_put_counter, cs);
+                                     (unsigned int *const *) d->d_flag_ptrs, d->n_flag, d->epoch, d->d_put_counter, 0, cs);
             CRP_MARK_ON(CRP_EV_PACKED, d->n_send_rows > 0 || d->n_flag > 0, cs);
         } else {
             mark[CRP_EV_PACKED] = mark[CRP_EV_B_IN];        /* the SpMM kernel stores the rows itself */
@@ -812,6 +911,7 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         }
     }
     CRP_MARK(CRP_EV_END, m > 0 && n > 0 && !C_direct);
+exec_enqueued: ;
 #undef CRP_MARK
 #undef CRP_MARK_ON
 

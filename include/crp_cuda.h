@@ -106,7 +106,7 @@ void  crp_cuda_put_rows(size_t dt_size, const int nrow, const int ncol, const vo
  * done_counter_d: one zero-initialised device word owned by the caller, reset by the kernel.  nrow == 0: only signals. */
 void  crp_cuda_put_rows_signal(
     size_t dt_size, const int nrow, const int ncol, const void *src, const int lds, const int *ridx_d, void *const *dst_rows_d,
-    unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, unsigned int *done_counter_d, void *stream
+    unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, unsigned int *done_counter_d, const size_t dst_off_bytes, void *stream
 );
 /* after the puts (same stream): *flag_ptrs_d[j] := epoch for j < nflag, with system-scope release */
 void  crp_cuda_signal_peers(unsigned int *const *flag_ptrs_d, const int nflag, const unsigned int epoch, void *stream);
@@ -165,6 +165,7 @@ typedef struct crp_exchange
     unsigned int epoch;
     double    timeout_s;
     int       *err;                         /* pinned host word set to 1 on timeout                          */
+    size_t    dst_off_bytes;                /* added to every destination address (a column block of wider rows) */
 } crp_exchange;
 void crp_cuda_spmm_exec_exchange(
     crp_spmm_plan *plan, const int n, const int elem_size, const double alpha,
@@ -177,9 +178,10 @@ void crp_cuda_spmm_set_wait_map(crp_spmm_plan *plan, const int nslot, const int 
 const char *crp_cuda_spmm_last_kernel(const crp_spmm_plan *plan);
 /* force a kernel variant for experiments: "auto", "rowsplit", "rowgroup", "panel", "mergepath" */
 void crp_cuda_spmm_set_variant(crp_spmm_plan *plan, const char *name);
-/* Column passes: a product whose window of live B / C rows does not fit the L2 is made in several passes over column blocks
- * of the dense operands (a multiple of 64 columns each), chosen per exec from the plan's reuse profile of the B rows.
- * set_passes forces the number (0: automatic; CRP_SPMM_PASSES does the same for every plan), last_passes reports it. */
+/* Column passes (opt-in): the product is made in several passes over column blocks of the dense operands (a multiple of 64
+ * columns each), so that the window of live B / C rows fits a small L2.  On B200 one pass measured fastest everywhere, so
+ * the default is 1; set_passes forces a count (0: default; CRP_SPMM_PASSES=<count> does the same for every plan,
+ * CRP_SPMM_PASSES=model decides from the plan's reuse profile of the B rows), last_passes reports what the last exec used. */
 void crp_cuda_spmm_set_passes(crp_spmm_plan *plan, const int passes);
 int crp_cuda_spmm_last_passes(const crp_spmm_plan *plan);
 /* host-only (no device needed): the number of passes the model picks for a CSR pattern, n columns of elem_size bytes, an L2 of l2_bytes */

@@ -95,3 +95,13 @@ def redist_layout(name):
 REDIST_CASES = ["rowblk_to_2x2", "2x3_to_3x2", "gather_to_0", "colblk_to_rowblk_8", "identity_3", "single"]
 REDIST_DIMS = {"rowblk_to_2x2": (37, 22), "2x3_to_3x2": (50, 41), "gather_to_0": (33, 18), "colblk_to_rowblk_8": (64, 40),
                "identity_3": (10, 7), "single": (9, 5)}
+
+
+# Deprecated composite engine (tests/golden/make_golden_crpspmm.py -> tests/golden/crpspmm_tables.json): name, matrix spec, n, nproc
+CRPSPMM_CASES = [
+    ("cmp_pwtk1500_np1_n32",  ("pwtk", 1500, 77000, 1200, 10), 32,  1),
+    ("cmp_pwtk1500_np4_n32",  ("pwtk", 1500, 77000, 1200, 10), 32,  4),     # 4 x 1
+    ("cmp_pwtk1500_np6_n512", ("pwtk", 1500, 77000, 1200, 10), 512, 6),     # 1 x 6
+    ("cmp_pwtk1500_np8_n128", ("pwtk", 1500, 77000, 1200, 10), 128, 8),
+    ("cmp_rand300_np4_n64",   ("rand", 300, 300, 7, 3, ()), 64, 4),
+]

@@ -11,13 +11,15 @@
 
 #include "rowgroup_build.hpp"
 
+static int g_cluster = 0;
+extern "C" void panel_emul_set_cluster(const int on) { g_cluster = on; }      // tiles by column overlap (crp_panel_cluster_tiles) or K consecutive groups
+
 extern "C" int panel_emul_spmm(
     const int m, const int k, const int *rowptr, const int *colidx, const double *val, const int n,
     const double *B, double *C, const int K, const int CR, const int EMAX, const double min_fill, const int forced_R,
     long long *stats   /* [0] R, [1] ngroups, [2] nblk, [3] rest rows, [4] ntiles, [5] nchunks, [6] union rows, [7] relaxed blocks, [8] meta bytes, [9] max rows / chunk, [10] max entries / chunk */
 )
 {
-    (void) k;
     for (int i = 0; i < 11; i++) stats[i] = 0;
     crp_rg_rowinfo ri;
     crp_rg_scan_rows(m, rowptr, colidx, &ri);
@@ -31,7 +33,17 @@ extern "C" int panel_emul_spmm(
         long long rest_nnz = 0;
         crp_rg_build(m, rowptr, colidx, val, ri, ch.R, ch.off, min_fill, &rh, &rest, &rest_nnz);
         crp_panel_host ph;
-        crp_panel_build_structure(rh, K, CR, EMAX, &ph);
+        std::vector<int> order;
+        if (g_cluster) crp_panel_cluster_tiles(rh, K, k, &order);
+        crp_panel_build_structure(rh, K, CR, EMAX, &ph, g_cluster ? &order : NULL);
+        if (g_cluster)
+        {
+            // every group in exactly one tile
+            std::vector<char> seen(rh.g_row.size(), 0);
+            if (order.size() != (size_t) ph.ntiles * K) return -30;
+            for (int g : order) { if (g < 0) continue; if (g >= (int) seen.size() || seen[g]) return -31; seen[g] = 1; }
+            for (char c : seen) if (!c) return -32;
+        }
         std::vector<unsigned char> meta;
         crp_panel_fill_meta<double>(rh, &ph, &meta);
         const int R = ch.R;

@@ -27,8 +27,9 @@ def emul(tmp_path_factory):
     return lib
 
 
-def run(emul, mat, n, K=8, CR=32, EMAX=128, fill=1.0, forced=0):
+def run(emul, mat, n, K=8, CR=32, EMAX=128, fill=1.0, forced=0, cluster=0):
     m, k, rp, ci, v = mat
+    emul.panel_emul_set_cluster(cluster)
     rp, ci = O.i32(rp), O.i32(ci)
     v = np.ascontiguousarray(v, dtype=np.float64)
     B = gen.fill_B(0, k, 0, n)
@@ -108,3 +109,25 @@ def test_forced_group_sizes(emul):
     for R in (2, 3, 6):
         s = run(emul, mat, 2, forced=R)
         assert s["R"] == R
+
+
+@pytest.mark.parametrize("which", ["pwtk", "stencil", "random", "misaligned"])
+def test_clustered_tiles(emul, which):
+    """Tiles formed by column overlap (crp_panel_cluster_tiles): every group in exactly one tile, the same bits as the CSR loop,
+    and - the point - smaller B row panels than tiles of K consecutive groups on mesh-like matrices."""
+    if which == "pwtk":
+        mat, kw = gen.pwtk_like(m=12000, target_nnz=632000, bandwidth=10000, grid_w=32, seed=11), {}
+    elif which == "stencil":
+        mat, kw = gen.stencil27(n=16), dict(fill=0.3)
+    elif which == "random":
+        mat, kw = gen.random_rect(300, 350, 6, seed=1), dict(fill=0.5)
+    else:
+        m, k, rp, ci, v = gen.pwtk_like(m=3000, target_nnz=150000, bandwidth=2500, grid_w=12, seed=3)
+        mat, kw = (m - 4, k, (rp[4:] - rp[4]).astype(np.int32), ci[rp[4]:], v[rp[4]:]), {}
+    seq = run(emul, mat, 4, cluster=0, **kw)
+    clu = run(emul, mat, 4, cluster=1, **kw)
+    assert (clu["R"], clu["ngroups"], clu["nblk"], clu["ntiles"]) == (seq["R"], seq["ngroups"], seq["nblk"], seq["ntiles"])
+    if which == "pwtk":
+        assert clu["union_rows"] < 0.9 * seq["union_rows"], (clu["union_rows"], seq["union_rows"])
+    if which == "stencil":
+        assert clu["union_rows"] < 0.75 * seq["union_rows"], (clu["union_rows"], seq["union_rows"])

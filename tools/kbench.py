@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--f32", action="store_true")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--rows", default="", help="a:b as fractions of m, e.g. 0.125:0.25 - time the kernel on a row slice (what one rank of several holds)")
+    ap.add_argument("--passes", default="0", help="comma list of column-pass counts to time per variant (0 = automatic)")
     ap.add_argument("--ldb0", action="store_true", help="experiment: leading dimension 0, every B row aliases row 0 (all gathers hit L1)")
     a = ap.parse_args()
     L = capi.load()
@@ -56,24 +57,26 @@ def main():
             os.environ[key] = val
         plan = L.crp_cuda_spmm_plan_create(m, k, k, capi.ptr(rp), capi.ptr(ci), capi.ptr(v), n)
         L.crp_cuda_spmm_set_variant(plan, parts[0].encode())
-        ts = []
-        for it in range(a.iters + 2):
-            L.crp_cuda_memset_async(dF.p, it, 256 << 20, stream)
-            L.crp_cuda_event_record(e0, stream)
-            L.crp_cuda_spmm_exec(plan, n, es, 1.0, dB.p, 0 if a.ldb0 else n, None, 0, 0.0, dC.p, n, stream)
-            L.crp_cuda_event_record(e1, stream)
-            L.crp_cuda_event_sync(e1)
-            if it >= 2:
-                ts.append(L.crp_cuda_event_elapsed_ms(e0, e1))
-        name = L.crp_cuda_spmm_last_kernel(plan).decode()
-        ms = float(np.median(ts))
-        out = {"spec": spec, "kernel": name, "ms_median": ms, "ms_min": min(ts), "gflops": 2.0 * nnz * n / ms / 1e6, "algo_gbs": algo / ms / 1e6, "n": n, "dtype": str(np.dtype(dt))}
-        if a.check:
-            Cd = dC.to_numpy((m, n), dt)
-            if ref is None:
-                ref = Cd
-            out["max_rel_diff_vs_first"] = float(np.max(np.abs(Cd.astype(np.float64) - ref) / (np.abs(ref) + 1e-300)))
-        print(json.dumps(out), flush=True)
+        for npass in (int(x) for x in a.passes.split(",")):
+            L.crp_cuda_spmm_set_passes(plan, npass)
+            ts = []
+            for it in range(a.iters + 2):
+                L.crp_cuda_memset_async(dF.p, it, 256 << 20, stream)
+                L.crp_cuda_event_record(e0, stream)
+                L.crp_cuda_spmm_exec(plan, n, es, 1.0, dB.p, 0 if a.ldb0 else n, None, 0, 0.0, dC.p, n, stream)
+                L.crp_cuda_event_record(e1, stream)
+                L.crp_cuda_event_sync(e1)
+                if it >= 2:
+                    ts.append(L.crp_cuda_event_elapsed_ms(e0, e1))
+            name = L.crp_cuda_spmm_last_kernel(plan).decode()
+            ms = float(np.median(ts))
+            out = {"spec": spec, "passes": L.crp_cuda_spmm_last_passes(plan), "kernel": name, "ms_median": ms, "ms_min": min(ts), "gflops": 2.0 * nnz * n / ms / 1e6, "algo_gbs": algo / ms / 1e6, "n": n, "dtype": str(np.dtype(dt))}
+            if a.check:
+                Cd = dC.to_numpy((m, n), dt)
+                if ref is None:
+                    ref = Cd
+                out["max_rel_diff_vs_first"] = float(np.max(np.abs(Cd.astype(np.float64) - ref) / (np.abs(ref) + 1e-300)))
+            print(json.dumps(out), flush=True)
         L.crp_cuda_spmm_plan_destroy(plan)
         for kv in parts[1:]:
             os.environ.pop(kv.split("=")[0], None)
