@@ -59,6 +59,23 @@ int crp_device_ready(void)
     return 1;
 }
 
+/* GPU-side plan construction (csrc/cuda/plan_build.cu) for matrices of at least CRP_SPMM_GPU_PLAN_MIN_NNZ nonzeros (default 2M:
+ * below that the copies cost more than the host loops), when a device is usable; CRP_SPMM_GPU_PLAN=0 keeps everything on the host.
+ * Never aborts: the partitioner can be used on a machine without a GPU. */
+int crp_gpu_plan_enabled(const long long nnz)
+{
+    static int on = -1, min_nnz = 0;
+    if (on < 0)
+    {
+        GET_ENV_INT_VAR(on, "CRP_SPMM_GPU_PLAN", "gpu_plan", 1, 0, 1, 0);
+        GET_ENV_INT_VAR(min_nnz, "CRP_SPMM_GPU_PLAN_MIN_NNZ", "gpu_plan_min_nnz", 2000000, 0, 2147483647, 0);
+    }
+    if (!on || nnz < (long long) min_nnz || nnz <= 0) return 0;
+    if (g_dev_state == 0 || crp_opt_plan_only()) return 0;
+    if (g_dev_state < 0 && crp_cuda_device_count() <= 0) return 0;
+    return crp_device_ready();
+}
+
 /* ---- pinned caller buffers ---- */
 typedef struct { const char *ptr; size_t bytes; } pin_entry;
 static pin_entry g_pins[64];

@@ -111,6 +111,8 @@ void rp_spmm_init_on(
     MPI_Comm nccl_parent, rp_spmm_p *rp_spmm
 );
 
+int crp_gpu_plan_enabled(const long long nnz);
+
 void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const int ldB, void *C, const int ldC, const int elem_size);
 
 #ifdef __cplusplus

@@ -75,38 +75,54 @@ static void rp_build_plan(
     const int nnz = A_rowptr[A_nrow] - nnz_base;
     const int glb_k = B_row_displs[nproc];
 
-    /* 1. column range of the local A, needed-row flags, compact copy of A */
-    int lo = INT_MAX, hi = 0;
-    for (int i = 0; i < nnz; i++)
-    {
-        const int c = A_colidx[i];
-        if (c < lo) lo = c;
-        if (c > hi) hi = c;
-    }
+    /* 1. column range of the local A, needed-row flags, compact copy of A.  Large blocks with a usable GPU: the three O(nnz)
+     *    sweeps (range, flags, re-indexing) and the prefix sum over the flags run on the device (csrc/cuda/plan_build.cu) and
+     *    return the re-indexed columns and the sorted list of needed rows; the flags are rebuilt from that list. */
     int *rowptr = (int *) xmalloc(sizeof(int) * ((size_t) A_nrow + 1));
     int *colidx = (int *) xmalloc(sizeof(int) * (size_t) nnz);
     double *val = (double *) xmalloc(sizeof(double) * (size_t) nnz);
     for (int i = 0; i <= A_nrow; i++) rowptr[i] = A_rowptr[i] - nnz_base;
     memcpy(val, A_val, sizeof(double) * (size_t) nnz);
-
     unsigned char *needed = (unsigned char *) xmalloc((size_t) glb_k);
     memset(needed, 0, (size_t) glb_k);
-    for (int i = 0; i < nnz; i++) needed[A_colidx[i]] = 1;
 
-    /* span == hi - lo + 1 also when nnz == 0 (the reference's INT_MAX arithmetic, kept for parity) */
-    int span = hi - lo + 1;
-    int rB_nrow = span;
+    int lo = INT_MAX, hi = 0, span, rB_nrow;
     int *pos_of = NULL;                 /* reidx: position in rB of global row lo + i */
-    if (reidx)
+    int gpu_n_needed = 0, *gpu_rows = NULL;
+    if (crp_gpu_plan_enabled((long long) nnz) &&
+        crp_cuda_plan_needed_rows(A_colidx, (long long) nnz, glb_k, reidx, colidx, &lo, &hi, &gpu_n_needed, &gpu_rows))
     {
-        pos_of = (int *) xmalloc(sizeof(int) * (size_t) (span > 0 ? span : 1));
-        int cnt = 0;
-        for (int g = 0; g < glb_k; g++)
-            if (needed[g]) pos_of[g - lo] = cnt++;
-        rB_nrow = cnt;
-        for (int i = 0; i < nnz; i++) colidx[i] = pos_of[A_colidx[i] - lo];
+        span = hi - lo + 1;
+        rB_nrow = reidx ? gpu_n_needed : span;
+        if (reidx) pos_of = (int *) xmalloc(sizeof(int) * (size_t) (span > 0 ? span : 1));
+        for (int j = 0; j < gpu_n_needed; j++)
+        {
+            needed[gpu_rows[j]] = 1;
+            if (reidx) pos_of[gpu_rows[j] - lo] = j;
+        }
+        free(gpu_rows);
     } else {
-        for (int i = 0; i < nnz; i++) colidx[i] = A_colidx[i] - lo;
+        for (int i = 0; i < nnz; i++)
+        {
+            const int c = A_colidx[i];
+            if (c < lo) lo = c;
+            if (c > hi) hi = c;
+        }
+        for (int i = 0; i < nnz; i++) needed[A_colidx[i]] = 1;
+        /* span == hi - lo + 1 also when nnz == 0 (the reference's INT_MAX arithmetic, kept for parity) */
+        span = hi - lo + 1;
+        rB_nrow = span;
+        if (reidx)
+        {
+            pos_of = (int *) xmalloc(sizeof(int) * (size_t) (span > 0 ? span : 1));
+            int cnt = 0;
+            for (int g = 0; g < glb_k; g++)
+                if (needed[g]) pos_of[g - lo] = cnt++;
+            rB_nrow = cnt;
+            for (int i = 0; i < nnz; i++) colidx[i] = pos_of[A_colidx[i] - lo];
+        } else {
+            for (int i = 0; i < nnz; i++) colidx[i] = A_colidx[i] - lo;
+        }
     }
     rp->A_rowptr = rowptr;
     rp->A_colidx = colidx;

@@ -16,6 +16,8 @@
 
 #include "spmat_part.h"
 #include "utils.h"
+#include "crp_cuda.h"
+#include "crp_internal.h"
 
 /* Row found by the reference's probe sequence for `target` in (rp[i] - base), i in [0, nrow):
  * a halving search that returns the probed row immediately on an exact hit
@@ -58,7 +60,9 @@ void csr_mat_row_part_comm_size(
     int *comm_sizes, int *total_size
 )
 {
-    (void) nrow;
+    /* large patterns with a usable GPU: bitmaps + popc on the device (csrc/cuda/plan_build.cu), same integers */
+    if (crp_gpu_plan_enabled((long long) row_ptr[rblk_ptr[nblk]] - row_ptr[rblk_ptr[0]]) &&
+        crp_cuda_part_comm_size(nrow, ncol, row_ptr, col_idx, nblk, rblk_ptr, x_displs, comm_sizes, total_size)) return;
     int nthr = omp_get_max_threads();
     if (nthr > nblk) nthr = nblk;
     if (nthr < 1) nthr = 1;
@@ -208,5 +212,6 @@ void calc_spmm_part2d_from_1d(
     free(cand_rows);
     free(x_split);
     free(per_blk);
+    if (crp_gpu_plan_enabled((long long) rowptr[m] - rowptr[0])) crp_cuda_part_cache_release();     /* the device copy of the pattern lives for this call only */
     free(fac);
 }

@@ -187,6 +187,18 @@ int crp_cuda_spmm_last_passes(const crp_spmm_plan *plan);
 /* host-only (no device needed): the number of passes the model picks for a CSR pattern, n columns of elem_size bytes, an L2 of l2_bytes */
 int crp_cuda_spmm_model_passes(const int m, const int k, const int *rowptr_h, const int *colidx_h, const int n, const int elem_size, const double l2_bytes);
 
+/* Device-side construction of the O(nnz) parts of the host plans (plan_build.cu); integers only, bit-identical to the host code.
+ * Both return 1 when they did the work, 0 when the caller must run its host loop (empty input, bitmaps too large).
+ *   crp_cuda_plan_needed_rows : colidx_out[i] = position of column colidx[i] among the distinct columns (reidx) or colidx[i] - lo;
+ *                               *needed_rows = malloc'ed ascending list of the distinct columns (caller frees), lo / hi = their range
+ *   crp_cuda_part_comm_size   : csr_mat_row_part_comm_size of include/spmat_part.h; the pattern is cached on the device between
+ *                               calls with the same arrays until crp_cuda_part_cache_release() */
+int crp_cuda_plan_needed_rows(const int *colidx_h, const long long nnz, const int glb_k, const int reidx,
+                              int *colidx_out_h, int *lo, int *hi, int *n_needed, int **needed_rows);
+int crp_cuda_part_comm_size(const int nrow, const int ncol, const int *row_ptr_h, const int *col_idx_h,
+                            const int nblk, const int *rblk_ptr_h, const int *x_displs_h, int *comm_sizes_h, int *total_size);
+void crp_cuda_part_cache_release(void);
+
 /* what the plan holds: out[0] group size R (1: none), [1] groups, [2] R x 1 blocks, [3] rows left to the row-split kernel,
  * [4] their nonzeros, [5] panel tiles, [6] panel chunks, [7] B rows staged per pass (sum of the tiles' unions), [8] 1 if all groups
  * are exact, [9] long rows cut into segments, [10] nnz, [11] merge-path chunks */
