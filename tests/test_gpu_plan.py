@@ -102,5 +102,8 @@ def test_engine_with_device_built_plans_matches_reference_golden(name, tmp_path)
             assert int(dumps[r][key]) == int(g[f"r{r}/{key}"][0]), (r, key)
         if mode == "2d":
             assert (int(dumps[r]["pm"]), int(dumps[r]["pn"])) == (int(g[f"r{r}/pm"][0]), int(g[f"r{r}/pn"][0]))
-            assert int(dumps[r]["comm_cost"]) == int(g[f"r{r}/comm_cost"][0])
+            if r == 0:                                                  # the reference driver computes the cost on rank 0 only
+                assert int(dumps[r]["comm_cost"]) == int(g[f"r{r}/comm_cost"][0])
+            for key in ("A0_rowptr", "B_rowptr", "AC_rowptr", "BC_colptr"):
+                assert np.array_equal(dumps[r][key], g[f"r{r}/{key}"]), (r, key)
     assert np.sqrt(num) <= 1e-12 * np.sqrt(den)
