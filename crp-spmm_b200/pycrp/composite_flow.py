@@ -2,6 +2,9 @@
 A in a 1-D row layout of the caller's choosing, B and C in an even 2-D block layout over a balanced process grid.
 
     minimpirun -np P python -m pycrp.composite_flow <csr.bin> <n> <prefix> [--no-exec] [--rowsplit even|nnz] [--gather-c]
+                                                   [--device] [--ntest N] [--json out.json] [--no-dump]
+--device keeps the caller's B and C blocks on the GPU (the redistributions then run device to device over NCCL / NVLink);
+--json makes rank 0 write the phase times of the timed execs and the redistribution bandwidth against the NVLink peak.
 
 Dumps per rank: the grid, the owned-rows CSR after the A redistribution (values included) and, unless --no-exec, the C block.
 """
@@ -38,6 +41,10 @@ def main(argv=None):
     ap.add_argument("--no-exec", action="store_true")
     ap.add_argument("--rowsplit", default="even", choices=["even", "skew"])
     ap.add_argument("--gather-c", action="store_true", help="rank 0 wants all of C (the reference driver's check mode)")
+    ap.add_argument("--device", action="store_true", help="the caller's B and C blocks are device buffers")
+    ap.add_argument("--ntest", type=int, default=2, help="number of execs (the first one builds the 2-D engine and is not timed)")
+    ap.add_argument("--json", default="", help="rank 0: write phase times / bandwidths of the timed execs here")
+    ap.add_argument("--no-dump", action="store_true")
     a = ap.parse_args(argv)
     rank, nproc = capi.mpi_init()
     L = capi.load()
@@ -74,15 +81,67 @@ def main(argv=None):
         L.crpspmm_engine_redist_A_values(eng, capi.ptr(loc_v))
         out["loc_A_val"] = capi.np_from(e.loc_A_val, e.loc_A_nnz, np.float64)
     else:
+        import json
+        import time
         B = np.ascontiguousarray(gen.fill_B(B_rect[0], B_rect[1], B_rect[2], B_rect[3]))
         Cb = np.zeros((C_rect[1], C_rect[3]))
-        for _ in range(2):          # second call reuses the engine (values unchanged)
-            L.crpspmm_engine_exec(eng, capi.ptr(loc_rp), capi.ptr(loc_ci), capi.ptr(loc_v), capi.ptr(B), max(B_rect[3], 1), capi.ptr(Cb), max(C_rect[3], 1))
+        if a.device:
+            dB, dC = capi.DevBuf.from_numpy(B), capi.DevBuf(max(Cb.nbytes, 8))
+            pB, pC = dB.p, dC.p
+        else:
+            pB, pC = capi.ptr(B), capi.ptr(Cb)
+        # the first call builds the 2-D engine (A redistribution + replicate-A) and is not timed; the later ones reuse it
+        L.crpspmm_engine_exec(eng, capi.ptr(loc_rp), capi.ptr(loc_ci), capi.ptr(loc_v), pB, max(B_rect[3], 1), pC, max(C_rect[3], 1))
+        t_first = dict(t_rd_A=e.t_rd_A, t_agv_A=e.t_agv_A, t_exec=e.t_exec)
+        L.crpspmm_engine_clear_stat(eng)
+        capi.mpi_barrier()
+        t0 = time.time()
+        for _ in range(max(a.ntest - 1, 1)):
+            L.crpspmm_engine_exec(eng, capi.ptr(loc_rp), capi.ptr(loc_ci), capi.ptr(loc_v), pB, max(B_rect[3], 1), pC, max(C_rect[3], 1))
+        capi.mpi_barrier()
+        wall = (time.time() - t0) / max(a.ntest - 1, 1)
+        if a.device:
+            Cb = dC.to_numpy(Cb.shape, np.float64) if Cb.size else Cb
         out["C"] = Cb
         out["loc_A_val"] = capi.np_from(e.loc_A_val, e.loc_A_nnz, np.float64)
         out["nelem"] = np.array([e.nelem_A_rd, e.nelem_A_agv, e.nelem_B_rd, e.nelem_B_a2av, e.nelem_B_a2av_min], dtype=np.uint64)
+        nx = max(e.n_exec, 1)
+        # bytes that really cross between GPUs in the two redistributions: what this rank receives from others
+        rdB, rdC = e.rd_B.contents, e.rd_C.contents
+        def foreign(rd):
+            tot = 0
+            for i in range(rd.n_proc_recv):
+                if rd.recv_ranks[i] != rank:
+                    tot += int(rd.recv_sizes[i])
+            return 8 * tot
+        mine = dict(rank=rank, t_rd_B=e.t_rd_B / nx, t_rd_C=e.t_rd_C / nx, t_a2a_B=e.t_a2a_B / nx, t_spmm=e.t_spmm / nx, t_exec_nr=e.t_exec_nr / nx,
+                    t_exec=e.t_exec / nx, rd_B_recv_bytes=foreign(rdB), rd_C_recv_bytes=foreign(rdC), wall=wall, first=t_first)
         L.crpspmm_engine_print_stat(eng)
-    np.savez(f"{a.prefix}.r{rank}.npz", **out)
+        if a.json:
+            with open(f"{a.json}.r{rank}", "w") as f:
+                json.dump(mine, f)
+            capi.mpi_barrier()
+            if rank == 0:
+                rows = [json.load(open(f"{a.json}.r{q}")) for q in range(nproc)]
+                peak = 770.0        # GB/s, measured peer copy (B200_PROFILING.md)
+                def bw(key_b, key_t):
+                    return max((r[key_b] / max(r[key_t], 1e-12) / 1e9) for r in rows)
+                summ = dict(nproc=nproc, grid=[int(e.np_row), int(e.np_col)], n=n, m=int(m), nnz=int(rowptr[-1]), device=bool(a.device),
+                            ms_per_exec=1e3 * max(r["wall"] for r in rows),
+                            phases_ms_max={k_: 1e3 * max(r[k_] for r in rows) for k_ in ("t_rd_B", "t_a2a_B", "t_spmm", "t_exec_nr", "t_rd_C", "t_exec")},
+                            first_exec_s={k_: max(r["first"][k_] for r in rows) for k_ in ("t_rd_A", "t_agv_A", "t_exec")},
+                            redist_B={"recv_MB_max": max(r["rd_B_recv_bytes"] for r in rows) / 1e6, "GBps_best_rank": bw("rd_B_recv_bytes", "t_rd_B"),
+                                      "nvlink_frac": bw("rd_B_recv_bytes", "t_rd_B") / peak},
+                            redist_C={"recv_MB_max": max(r["rd_C_recv_bytes"] for r in rows) / 1e6, "GBps_best_rank": bw("rd_C_recv_bytes", "t_rd_C"),
+                                      "nvlink_frac": bw("rd_C_recv_bytes", "t_rd_C") / peak},
+                            gflops=2.0 * float(rowptr[-1]) * n / max(r["wall"] for r in rows) / 1e9, per_rank=rows)
+                with open(a.json, "w") as f:
+                    json.dump(summ, f)
+                print("COMPOSITE " + json.dumps({k_: v_ for k_, v_ in summ.items() if k_ != "per_rank"}), flush=True)
+    if a.no_dump:
+        out = {}
+    if not a.no_dump:
+        np.savez(f"{a.prefix}.r{rank}.npz", **out)
     L.crpspmm_engine_free(C.byref(eng))
     capi.mpi_barrier()
     capi.mpi_finalize()
