@@ -59,6 +59,22 @@ int crp_device_ready(void)
     return 1;
 }
 
+/* Ranks of this job that run on this node (they share its GPUs): what the launcher says, else the world size (single node). */
+int crp_ranks_on_this_node(const int world_size)
+{
+    static const char *names[] = { "OMPI_COMM_WORLD_LOCAL_SIZE", "MV2_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "SLURM_NTASKS_PER_NODE", "LOCAL_WORLD_SIZE" };
+    for (size_t i = 0; i < sizeof(names) / sizeof(names[0]); i++)
+    {
+        const char *e = getenv(names[i]);
+        if (e != NULL && e[0] >= '1' && e[0] <= '9')
+        {
+            const int v = atoi(e);
+            if (v >= 1 && v <= world_size) return v;
+        }
+    }
+    return world_size;
+}
+
 /* GPU-side plan construction (csrc/cuda/plan_build.cu) for matrices of at least CRP_SPMM_GPU_PLAN_MIN_NNZ nonzeros (default 2M:
  * below that the copies cost more than the host loops), when a device is usable; CRP_SPMM_GPU_PLAN=0 keeps everything on the host.
  * Never aborts: the partitioner can be used on a machine without a GPU. */

@@ -112,6 +112,7 @@ void rp_spmm_init_on(
 );
 
 int crp_gpu_plan_enabled(const long long nnz);
+int crp_ranks_on_this_node(const int world_size);
 
 void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const int ldB, void *C, const int ldC, const int elem_size);
 

@@ -135,7 +135,7 @@ void mat_redist_engine_init(
         int wsize = 1, transport;
         MPI_Comm_size(MPI_COMM_WORLD, &wsize);
         GET_ENV_INT_VAR(transport, "CRP_SPMM_TRANSPORT", "transport", -1, 0, 1, 0);
-        if (transport < 0) transport = (wsize > crp_cuda_device_count()) ? 1 : 0;
+        if (transport < 0) transport = (crp_ranks_on_this_node(wsize) > crp_cuda_device_count()) ? 1 : 0;
         d->staged = transport;
         if (nproc > 1 && !d->staged) d->nc = crp_nccl_get(comm);
     }

@@ -66,7 +66,7 @@ static void grow_host(void **buf, size_t *cap, size_t need)
  */
 static void rp_build_plan(
     rp_spmm_p rp, const int A_nrow, const int *A_rowptr, const int *A_colidx, const double *A_val,
-    const int *B_row_displs, const int glb_n, MPI_Comm comm
+    const int *B_row_displs, const int glb_n, MPI_Comm comm, int **send_row_cnt, int **recv_row_cnt
 )
 {
     const int nproc = rp->nproc, me = rp->my_rank;
@@ -180,6 +180,10 @@ static void rp_build_plan(
     /* 5. global ids -> positions (receive side: in rB; send side: in the own B block); counts in elements */
     for (int i = 0; i < nreq; i++) rridxs[i] = reidx ? pos_of[rridxs[i] - lo] : rridxs[i] - lo;
     for (int i = 0; i < sdispls[nproc]; i++) sridxs[i] -= my_lo;
+    /* rows per peer, kept apart: the public counts below are rows * glb_n in int arithmetic (the reference's) and may wrap */
+    *send_row_cnt = (int *) xmalloc(sizeof(int) * (size_t) nproc);
+    *recv_row_cnt = (int *) xmalloc(sizeof(int) * (size_t) nproc);
+    for (int p = 0; p < nproc; p++) { (*send_row_cnt)[p] = scnts[p]; (*recv_row_cnt)[p] = rcnts[p]; }
     for (int p = 0; p < nproc; p++)
     {
         rcnts[p] *= glb_n;  rdispls[p] *= glb_n;
@@ -334,7 +338,7 @@ static void rp_p2p_teardown(rp_spmm_p rp, struct crp_rp_dev *d)
  * row counts kept in 64 bits (the public int counts are rows * glb_n and may
  * wrap for very wide B, as they do in the reference).
  */
-static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Comm nccl_parent)
+static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Comm nccl_parent, const int *send_row_cnt, const int *recv_row_cnt)
 {
     struct crp_rp_dev *d = (struct crp_rp_dev *) calloc(1, sizeof(struct crp_rp_dev));
     ASSERT_PRINTF(d != NULL, "Failed to allocate device state for rp_spmm\n");
@@ -343,14 +347,14 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     const int nnz = rp->A_rowptr[rp->A_nrow];
     d->nB = B_row_displs[me + 1] - B_row_displs[me];
 
-    /* row counts per peer (exact division: counts were rows * n) */
+    /* row counts per peer, as counted by the plan (not recovered from the element counts, which may have wrapped) */
     d->send_rows = (int *) xmalloc(sizeof(int) * ((size_t) nproc + 1));
     d->recv_rows = (int *) xmalloc(sizeof(int) * ((size_t) nproc + 1));
     d->send_rows[0] = d->recv_rows[0] = 0;
     for (int p = 0; p < nproc; p++)
     {
-        d->send_rows[p + 1] = d->send_rows[p] + (n > 0 ? rp->rB_scnts[p] / n : 0);
-        d->recv_rows[p + 1] = d->recv_rows[p] + (n > 0 ? rp->rB_rcnts[p] / n : 0);
+        d->send_rows[p + 1] = d->send_rows[p] + (n > 0 ? send_row_cnt[p] : 0);
+        d->recv_rows[p + 1] = d->recv_rows[p] + (n > 0 && p != rp->my_rank ? recv_row_cnt[p] : 0);
     }
     d->n_send_rows = d->send_rows[nproc];
     d->n_recv_rows = d->recv_rows[nproc];
@@ -406,7 +410,7 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
      * kernels of different processes on ONE GPU must never spin on each other (nothing guarantees that they run at the
      * same time), so the arrival of the rows is established by a host barrier after the put kernels have completed
      * ("hostsync"); the flags are still written, and read (already satisfied) by the SpMM kernel. */
-    const int shared_gpu = (wsize > crp_cuda_device_count());
+    const int shared_gpu = (crp_ranks_on_this_node(wsize) > crp_cuda_device_count());
     if (shared_gpu && transport != 2) transport = 1;
     else if (transport < 0) transport = CRP_DEFAULT_TRANSPORT;
     d->staged = (transport == 1);
@@ -471,10 +475,18 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     if (d->p2p) d->p2p = rp_p2p_setup(rp, d);
     if (!d->p2p) d->p2p_hostsync = 0;
     if (!d->p2p && shared_gpu) d->staged = 1;
-    if (nproc > 1 && !d->staged && !d->p2p)
+    /* NCCL for the exchange: creating the communicator is collective over nccl_parent (the whole grid), the peer-memory
+     * decision above was taken per grid column - so every member learns whether ANY column needs NCCL and joins the creation */
+    int need_nccl = (nproc > 1 && !d->staged && !d->p2p) ? 1 : 0, any_nccl = need_nccl;
+    if (!shared_gpu && nccl_parent != MPI_COMM_NULL) MPI_Allreduce(&need_nccl, &any_nccl, 1, MPI_INT, MPI_MAX, nccl_parent);
+    if (any_nccl)
     {
-        d->nc = crp_nccl_get(nccl_parent);
-        d->peer_nc_rank = crp_comm_ranks_in_parent(rp->comm, nccl_parent);
+        crp_nccl_comm *nc = crp_nccl_get(nccl_parent);
+        if (need_nccl)
+        {
+            d->nc = nc;
+            d->peer_nc_rank = crp_comm_ranks_in_parent(rp->comm, nccl_parent);
+        }
     }
 }
 
@@ -536,8 +548,11 @@ void rp_spmm_init_on(
     GET_ENV_INT_VAR(rp->rB_p2p,   "RP_SPMM_P2P",   "rB_p2p",   1, 0, 1, wrank == 0);
     GET_ENV_INT_VAR(rp->rB_reidx, "RP_SPMM_REIDX", "rB_reidx", 1, 0, 1, wrank == 0);
 
-    rp_build_plan(rp, A_nrow, A_rowptr, A_colidx, A_val, B_row_displs, glb_n, comm);
-    if (crp_device_ready()) rp_build_device_state(rp, B_row_displs, nccl_parent);
+    int *send_row_cnt = NULL, *recv_row_cnt = NULL;
+    rp_build_plan(rp, A_nrow, A_rowptr, A_colidx, A_val, B_row_displs, glb_n, comm, &send_row_cnt, &recv_row_cnt);
+    if (crp_device_ready()) rp_build_device_state(rp, B_row_displs, nccl_parent, send_row_cnt, recv_row_cnt);
+    free(send_row_cnt);
+    free(recv_row_cnt);
 
     rp->t_init = get_wtime_sec() - t0;
     *rp_spmm = rp;
