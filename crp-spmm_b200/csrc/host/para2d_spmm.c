@@ -34,7 +34,7 @@ static void *xmalloc(size_t bytes)
 /* pool colidx / val of the grid row on the devices; results land in the host arrays */
 static void pool_panel_nccl(
     MPI_Comm comm, const int pi, const int pj, const int pn, const int *nnz_displs,
-    const int *A_colidx, const double *A_val, int *panel_colidx, double *panel_val
+    const int *A_colidx, const double *A_val, int *panel_colidx, double *panel_val, double *t_dev, size_t *recv_bytes
 )
 {
     const size_t tot = (size_t) nnz_displs[pn];
@@ -50,6 +50,8 @@ static void pool_panel_nccl(
         crp_cuda_memcpy_async(A_colidx, (char *) d_col + sizeof(int) * (size_t) nnz_displs[pj], sizeof(int) * mine, stream);
         crp_cuda_memcpy_async(A_val, (char *) d_val + sizeof(double) * (size_t) nnz_displs[pj], sizeof(double) * mine, stream);
     }
+    void *e0 = crp_cuda_event_create(), *e1 = crp_cuda_event_create();
+    crp_cuda_event_record(e0, stream);
     crp_nccl_group_start();
     for (int j = 0; j < pn; j++)
     {
@@ -68,9 +70,14 @@ static void pool_panel_nccl(
         }
     }
     crp_nccl_group_end();
+    crp_cuda_event_record(e1, stream);
     crp_cuda_memcpy_async(d_col, panel_colidx, sizeof(int) * tot, stream);
     crp_cuda_memcpy_async(d_val, panel_val, sizeof(double) * tot, stream);
     crp_cuda_stream_sync(stream);
+    *t_dev += 1e-3 * crp_cuda_event_elapsed_ms(e0, e1);
+    *recv_bytes += (sizeof(int) + sizeof(double)) * (tot - mine);
+    crp_cuda_event_destroy(e0);
+    crp_cuda_event_destroy(e1);
     crp_cuda_stream_destroy(stream);
     crp_cuda_free_dev(d_col);
     crp_cuda_free_dev(d_val);
@@ -138,7 +145,7 @@ void para2d_spmm_init(
         if (transport < 0) transport = (crp_device_ready() && wsize <= crp_cuda_device_count()) ? 0 : 1;
         if (transport == 0 && crp_device_ready())
         {
-            pool_panel_nccl(comm, pi, pj, pn, displs, A_colidx, A_val, panel_colidx, panel_val);
+            pool_panel_nccl(comm, pi, pj, pn, displs, A_colidx, A_val, panel_colidx, panel_val, &eng->t_ag_A_dev, &eng->ag_A_recv_bytes);
         } else {
             MPI_Allgatherv(A_colidx, my_nnz, MPI_INT, panel_colidx, cnts, displs, MPI_INT, comm_row);
             MPI_Allgatherv(A_val, my_nnz, MPI_DOUBLE, panel_val, cnts, displs, MPI_DOUBLE, comm_row);

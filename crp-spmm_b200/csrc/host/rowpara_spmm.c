@@ -696,8 +696,8 @@ static int rp_e2e_panel_count(rp_spmm_p rp, struct crp_rp_dev *d, const int BC_l
     const int n = rp->glb_n;
     int P = want;
     while (P > 1 && n / P < 32) P--;
-    /* a panel starts on a 16-byte boundary in both types: multiples of 4 columns */
-    int ok = (P > 1) && BC_layout == 0 && !B_on_dev && !C_on_dev && rp->A_nrow > 0 && d->nB > 0 && (n % 4 == 0);
+    /* panels start on 64-byte boundaries: multiples of 8 columns */
+    int ok = (P > 1) && BC_layout == 0 && !B_on_dev && !C_on_dev && rp->A_nrow > 0 && d->nB > 0 && (n % 8 == 0);
     if (rp->nproc > 1)
     {
         /* every rank must cut the call the same way (each panel is an exchange round); only the fused peer-memory route */
@@ -751,23 +751,34 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         grow_dev(&d->d_Bwork, &d->Bwork_bytes, row_bytes * (size_t) nB);
         grow_dev(&d->d_Cwork, &d->Cwork_bytes, row_bytes * (size_t) m);
         if (d->p2p) rp_p2p_tables(rp, d, elem_size);
-        const int pw = ((n + npanel - 1) / npanel + 3) / 4 * 4;         /* panel width in columns */
-        crp_cuda_stream_wait_event(d->stream_in, mark[CRP_EV_START]);
-        int np = 0;
-        for (int c0 = 0; c0 < n; c0 += pw, np++)
+        /* panel boundaries: equal panels except the LAST, which is about half as wide - what follows the last H2D (its
+         * product and its D2H) is the only part of the call that nothing hides.  Multiples of 8 columns (64-byte segments). */
+        int pcol[CRP_E2E_MAX_PANELS + 1];
         {
-            const int w = (n - c0 < pw) ? n - c0 : pw;
+            static int taper = -1;
+            if (taper < 0) GET_ENV_INT_VAR(taper, "CRP_SPMM_E2E_TAPER", "e2e_taper", 1, 0, 1, 0);
+            int base = taper ? (int) ((2ll * n) / (2 * npanel - 1)) : (n + npanel - 1) / npanel;
+            base = taper ? base / 8 * 8 : (base + 7) / 8 * 8;
+            if (base < 8) base = 8;
+            pcol[0] = 0;
+            for (int j = 1; j < npanel; j++) { pcol[j] = pcol[j - 1] + base; if (pcol[j] > n) pcol[j] = n; }
+            pcol[npanel] = n;
+        }
+        crp_cuda_stream_wait_event(d->stream_in, mark[CRP_EV_START]);
+        for (int np = 0; np < npanel; np++)
+        {
+            const int c0 = pcol[np], w = pcol[np + 1] - c0;
             const size_t off = es * (size_t) c0;
-            crp_cuda_memcpy2d_async((const char *) B + off, es * (size_t) ldB, (char *) d->d_Bwork + off, row_bytes, es * (size_t) w, (size_t) nB, d->stream_in);
+            if (w > 0) crp_cuda_memcpy2d_async((const char *) B + off, es * (size_t) ldB, (char *) d->d_Bwork + off, row_bytes, es * (size_t) w, (size_t) nB, d->stream_in);
             crp_cuda_event_record(d->ev_in[np], d->stream_in);
         }
-        np = 0;
-        for (int c0 = 0; c0 < n; c0 += pw, np++)
+        for (int np = 0; np < npanel; np++)
         {
-            const int w = (n - c0 < pw) ? n - c0 : pw;
+            const int c0 = pcol[np], w = pcol[np + 1] - c0;
             const size_t off = es * (size_t) c0;
             crp_cuda_stream_wait_event(stream, d->ev_in[np]);
             if (np == 0) { crp_cuda_event_record(ev[CRP_EV_B_IN], stream); mark[CRP_EV_B_IN] = ev[CRP_EV_B_IN]; }
+            if (w <= 0) continue;                   /* every rank skips the same (empty) panels: no exchange round is lost */
             if (d->p2p)
             {
                 d->epoch++;

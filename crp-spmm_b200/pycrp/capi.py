@@ -59,6 +59,7 @@ class Para2dSpmm(C.Structure):
     _fields_ = [
         ("rp_spmm", C.POINTER(RowparaSpmm)), ("comm_glb", C.c_int), ("comm_col", C.c_int),
         ("rA_cost", C.c_size_t), ("t_init", C.c_double), ("t_ag_A", C.c_double),
+        ("t_ag_A_dev", C.c_double), ("ag_A_recv_bytes", C.c_size_t),
     ]
 
 

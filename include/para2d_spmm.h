@@ -24,6 +24,9 @@ struct para2d_spmm
     size_t    rA_cost;      /* modelled volume of replicating A (valid on rank 0)        */
     double    t_init;       /* seconds in para2d_spmm_init outside the A replication     */
     double    t_ag_A;       /* seconds replicating A                                     */
+    /* ---- additions of this implementation ---- */
+    double    t_ag_A_dev;   /* of which: the NCCL exchange between the GPUs of the grid row (device time, CUDA events) */
+    size_t    ag_A_recv_bytes;  /* bytes of colidx / val this rank received in it                */
 };
 typedef struct para2d_spmm  para2d_spmm_s;
 typedef struct para2d_spmm *para2d_spmm_p;
