@@ -95,6 +95,7 @@ struct crp_panel
     unsigned char *d_meta[2];
     size_t    meta_bytes[2];
     unsigned  *d_chunk_need;    // multi-GPU: wait slots each chunk depends on (NULL: none)
+    long long *d_trace;         // development aid (CRP_PANEL_TRACE), not owned
     int       nslot;
 };
 

@@ -23,6 +23,7 @@
 // bandwidth (fill + R-fold reuse reads) and fp64 issue inside the SM.  DESIGN.md has the numbers.
 #include <cstring>
 #include <vector>
+#include <unistd.h>
 
 #include "crp_cuda_internal.cuh"
 #include "panel_build.hpp"
@@ -156,6 +157,14 @@ __device__ __forceinline__ void lds_vals_s(const unsigned addr, T (&a)[R])
 
 enum { CRP_PANEL_MAXSTAGE = 8, CRP_PANEL_BAR_BYTES = 128 };
 
+__device__ __forceinline__ long long gtime_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CRP_TRACE(slot) do { if (a.trace != NULL && lane == 0) a.trace[(size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime_ns(); } while (0)
+
 template <typename T>
 struct panel_args
 {
@@ -196,6 +205,7 @@ struct panel_args
     unsigned epoch;
     long long timeout_ns;
     int *err;
+    long long *trace;                   // development aid (CRP_PANEL_TRACE): 8 time stamps per block, NULL in production
 };
 
 // FAST: every column slice is full (n is a multiple of the slice width) and all groups are exact - no bounds predicates,
@@ -230,6 +240,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
     const int col0 = blockIdx.y * W;
     const int ncols = min(a.n - col0, W);
 
+    if (warp == 0) CRP_TRACE(0);                            // block start
     if (threadIdx.x == 0)
     {
         for (int s = 0; s < nstage; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K); }
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
             *a.put_counter = 0u;
         }
     }
+    if (warp == 0) CRP_TRACE(1);                            // this block's share of the put is done (and counted)
 
     if (warp < PW)
     {
@@ -353,6 +365,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
                 need &= ~seen;
                 if (need)
                 {
+                    const long long tw0 = (a.trace != NULL) ? gtime_ns() : 0;
                     // one lane per missing neighbour spins on its arrival flag; the rows were written by the peer's stores
                     // before the flag (fence + st.release.sys on the sender)
                     if (lane < a.nwait && ((need >> lane) & 1u))
@@ -371,9 +384,21 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
                     __syncwarp();
                     asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy acquire -> async-proxy (TMA) reads
                     seen |= need;
+                    if (warp == 0 && a.trace != NULL && lane == 0)
+                    {
+                        const size_t tb = (size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8;
+                        a.trace[tb + 4] += gtime_ns() - tw0;                    // time this producer spent waiting for flags
+                        if (a.trace[tb + 6] == 0) a.trace[tb + 6] = tw0;        // when it first had to wait
+                    }
                 }
             }
             mbar_wait(&empty[s], ph);
+            if (warp == 0 && a.trace != NULL && lane == 0)
+            {
+                const size_t tb = (size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8;
+                if (a.trace[tb + 2] == 0) a.trace[tb + 2] = gtime_ns();         // first chunk issued
+                if (is_stop) a.trace[tb + 7] = gtime_ns();                      // stop record issued (all flags seen)
+            }
             if (lane == 0) mbar_arrive_expect_tx(&full[s], (unsigned) nrows * rb + mbytes);
             __syncwarp();
             if (lane == 0) bulk_g2s(metas + (size_t) s * a.meta_max, a.meta + (size_t) mo16 * 16, mbytes, &full[s]);
@@ -508,6 +533,12 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
     for (;; s = (s + 1 == nstage) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u)
     {
         mbar_wait(&full[s], ph);
+        if (w == 0 && a.trace != NULL && lane == 0)
+        {
+            const size_t tb = (size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8;
+            if (a.trace[tb + 3] == 0) a.trace[tb + 3] = gtime_ns();             // first chunk landed
+            a.trace[tb + 5] = gtime_ns();                                       // last chunk (or the stop record) seen
+        }
         const unsigned mrec = metas_s + (unsigned) s * a.meta_max;
         // all header words at once (one shared-memory round trip), then the stop test
         const int flags = (int) lds_u32(mrec + 4);
@@ -693,6 +724,29 @@ static void panel_make_meta(crp_spmm_plan *plan)
 void crp_panel_destroy(crp_spmm_plan *plan)
 {
     crp_panel *pn = &plan->pn;
+    if (pn->d_trace != NULL)
+    {
+        std::vector<long long> t((size_t) 8 * 1024);
+        CRP_CUDA_CHECK(cudaDeviceSynchronize());
+        CRP_CUDA_CHECK(cudaMemcpy(t.data(), pn->d_trace, sizeof(long long) * t.size(), cudaMemcpyDeviceToHost));
+        char path[512];
+        snprintf(path, sizeof(path), "%s.%d", getenv("CRP_PANEL_TRACE"), (int) getpid());
+        FILE *f = fopen(path, "w");
+        if (f != NULL)
+        {
+            fprintf(f, "# block start put_done first_issue first_landed flag_wait_ns last_seen first_wait_at stop_issued   (ns, relative to the earliest block start)\n");
+            long long t0 = 0;
+            for (size_t b = 0; b < 1024; b++) if (t[8 * b] != 0 && (t0 == 0 || t[8 * b] < t0)) t0 = t[8 * b];
+            for (size_t b = 0; b < 1024; b++)
+            {
+                if (t[8 * b] == 0) continue;
+                fprintf(f, "%zu", b);
+                for (int j = 0; j < 8; j++) fprintf(f, " %lld", (j == 4 || t[8 * b + j] == 0) ? t[8 * b + j] : t[8 * b + j] - t0);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     if (pn->d_tile_chunk_ptr) CRP_CUDA_CHECK(cudaFree(pn->d_tile_chunk_ptr));
     if (pn->d_ucol) CRP_CUDA_CHECK(cudaFree(pn->d_ucol));
     if (pn->d_chunk_need) CRP_CUDA_CHECK(cudaFree(pn->d_chunk_need));
@@ -852,6 +906,20 @@ bool crp_launch_panel(
         a.put_nrow = put->nrow;  a.put_row_bytes = (unsigned) put->row_bytes;  a.put_ridx = put->ridx;
         a.put_dst_rows = (char *const *) put->dst_rows;  a.put_flag_ptrs = put->flag_ptrs;  a.put_nflag = put->nflag;
         a.put_counter = put->counter;  a.epoch = put->epoch;  a.put_dst_off = put->dst_off;
+    }
+    {
+        // development aid: CRP_PANEL_TRACE=<file prefix> records 8 time stamps per block of every launch (the last one is
+        // written to <prefix>.<pid> when the plan is destroyed); costs a few predicated stores, off by default
+        static long long *d_trace = NULL;
+        static int trace_on = -1;
+        if (trace_on < 0) { const char *e = getenv("CRP_PANEL_TRACE"); trace_on = (e && e[0]) ? 1 : 0; }
+        if (trace_on)
+        {
+            if (d_trace == NULL) CRP_CUDA_CHECK(cudaMalloc((void **) &d_trace, sizeof(long long) * 8 * 1024));
+            CRP_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 1024, s));
+            a.trace = d_trace;
+            pn->d_trace = d_trace;
+        }
     }
     switch (pn->R)
     {

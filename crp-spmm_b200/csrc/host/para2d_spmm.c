@@ -50,6 +50,22 @@ static void pool_panel_nccl(
         crp_cuda_memcpy_async(A_colidx, (char *) d_col + sizeof(int) * (size_t) nnz_displs[pj], sizeof(int) * mine, stream);
         crp_cuda_memcpy_async(A_val, (char *) d_val + sizeof(double) * (size_t) nnz_displs[pj], sizeof(double) * mine, stream);
     }
+    /* a tiny exchange with the same peers first: NCCL sets its connections up lazily on the first transfer between two ranks
+     * (about a second for a fresh communicator) - that is not replication time */
+    {
+        void *d_warm = NULL;
+        crp_cuda_malloc_dev(&d_warm, 64 * (size_t) pn);
+        crp_nccl_group_start();
+        for (int j = 0; j < pn; j++)
+        {
+            if (j == pj) continue;
+            crp_nccl_send(nc, (char *) d_warm + 64 * (size_t) pj, 32, pi * pn + j, stream);
+            crp_nccl_recv(nc, (char *) d_warm + 64 * (size_t) j + 32, 32, pi * pn + j, stream);
+        }
+        crp_nccl_group_end();
+        crp_cuda_stream_sync(stream);
+        crp_cuda_free_dev(d_warm);
+    }
     void *e0 = crp_cuda_event_create(), *e1 = crp_cuda_event_create();
     crp_cuda_event_record(e0, stream);
     crp_nccl_group_start();

@@ -61,3 +61,21 @@ def test_forced_group_size(monkeypatch):
     assert analyse(rp, ci)[0] == 3
     monkeypatch.setenv("CRP_SPMM_ROWGROUP_R", "1")
     assert analyse(rp, ci)[0] == 1
+
+
+def test_ranks_per_node_follows_the_launcher(monkeypatch):
+    """Transport selection compares the ranks on THIS node (not the world size) with the visible GPUs, so that multi-node jobs
+    with one rank per GPU keep the device transports (crp_ranks_on_this_node, csrc/host/crp_common.c)."""
+    import ctypes as C
+    L = capi.load()
+    L.crp_ranks_on_this_node.argtypes = [C.c_int]
+    L.crp_ranks_on_this_node.restype = C.c_int
+    for var in ("OMPI_COMM_WORLD_LOCAL_SIZE", "MV2_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "SLURM_NTASKS_PER_NODE", "LOCAL_WORLD_SIZE"):
+        monkeypatch.delenv(var, raising=False)
+    assert L.crp_ranks_on_this_node(16) == 16            # nothing known: single node
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert L.crp_ranks_on_this_node(16) == 8
+    monkeypatch.setenv("OMPI_COMM_WORLD_LOCAL_SIZE", "4")
+    assert L.crp_ranks_on_this_node(16) == 4
+    monkeypatch.setenv("OMPI_COMM_WORLD_LOCAL_SIZE", "64")     # nonsense (more than the world): ignored
+    assert L.crp_ranks_on_this_node(16) == 8
