@@ -246,33 +246,38 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
         for (int s = 0; s < nstage; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (a.put_nflag > 0)
+    __syncthreads();                                        // barriers initialised
+    if (a.put_nflag > 0 && warp >= PW)
     {
-        // fused "pack + send" (reference src/rowpara_spmm.c:232-301): 128-bit loads of the own B rows, 128-bit stores over NVLink
+        // Fused "pack + send" (reference src/rowpara_spmm.c:232-301): 128-bit loads of the own B rows, 128-bit stores over NVLink,
+        // by the consumer and rest warps ONLY - they have nothing to multiply until the first chunk has landed, while the
+        // producers start their descriptor chain at once.  (Round-2 trace, profiles/r02_trace_n2.txt: with all warps putting and
+        // a block-wide barrier behind the system fence, the first chunk landed 15 us after the block started instead of 6.)
+        constexpr unsigned NPUT = (K + 1) * 32;             // putting threads per block
         const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned tid = threadIdx.x - PW * 32;
         const unsigned vpr = a.put_row_bytes / 16u;
         const size_t total = (size_t) a.put_nrow * vpr;
-        for (size_t t = (size_t) bid * blockDim.x + threadIdx.x; t < total; t += (size_t) nblocks * blockDim.x)
+        for (size_t t = (size_t) bid * NPUT + tid; t < total; t += (size_t) nblocks * NPUT)
         {
             const unsigned r = (unsigned) (t / vpr), v = (unsigned) (t - (size_t) r * vpr);
             const uint4 val = *reinterpret_cast<const uint4 *>(a.X0 + (size_t) a.put_ridx[r] * a.ldx0 + (size_t) v * 16);
             *reinterpret_cast<uint4 *>(a.put_dst_rows[r] + a.put_dst_off + (size_t) v * 16) = val;
         }
         __threadfence_system();
-    }
-    __syncthreads();
-    if (a.put_nflag > 0 && threadIdx.x == 0)
-    {
-        const unsigned nblocks = gridDim.x * gridDim.y;
-        if (atomicAdd(a.put_counter, 1u) == nblocks - 1u)
+        asm volatile("bar.sync 1, %0;" :: "r"(NPUT) : "memory");          // the putting warps only
+        if (tid == 0)
         {
-            __threadfence();                    // the other blocks' stores (fenced before their atomicAdd) come before the flags
-            for (int j = 0; j < a.put_nflag; j++)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.put_flag_ptrs[j]), "r"(a.epoch) : "memory");
-            *a.put_counter = 0u;
+            if (atomicAdd(a.put_counter, 1u) == nblocks - 1u)
+            {
+                __threadfence();                // the other blocks' stores (fenced before their atomicAdd) come before the flags
+                for (int j = 0; j < a.put_nflag; j++)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.put_flag_ptrs[j]), "r"(a.epoch) : "memory");
+                *a.put_counter = 0u;
+            }
+            if (a.trace != NULL) a.trace[(size_t) bid * 8 + 1] = gtime_ns();    // this block's share of the put is done (and counted)
         }
     }
-    if (warp == 0) CRP_TRACE(1);                            // this block's share of the put is done (and counted)
 
     if (warp < PW)
     {

@@ -16,3 +16,4 @@ PY
 ENVV="CRP_PANEL_TRACE=gpurun_out/r2s2_trace_n2" run_bench n2 2
 ENVV="CRP_X=1" run_bench n2_notrace 2
 ls gpurun_out | grep trace_n2 | head
+( timeout 600 python -m pytest tests/test_gpu_panel.py tests/test_gpu_transports.py -m gpu -q --tb=short --timeout 240 -x -k "not np8" 2>&1 | tail -n 4 ) > gpurun_out/r2s2_pytest_put.log; tail -n 3 gpurun_out/r2s2_pytest_put.log
