@@ -249,33 +249,53 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
     __syncthreads();                                        // barriers initialised
     if (a.put_nflag > 0 && warp >= PW)
     {
-        // Fused "pack + send" (reference src/rowpara_spmm.c:232-301): 128-bit loads of the own B rows, 128-bit stores over NVLink,
-        // by the consumer and rest warps ONLY - they have nothing to multiply until the first chunk has landed, while the
-        // producers start their descriptor chain at once.  (Round-2 trace, profiles/r02_trace_n2.txt: with all warps putting and
-        // a block-wide barrier behind the system fence, the first chunk landed 15 us after the block started instead of 6.)
-        constexpr unsigned NPUT = (K + 1) * 32;             // putting threads per block
+        // Fused "pack + send" (reference src/rowpara_spmm.c:232-301): 128-bit loads of the own B rows, 128-bit stores over NVLink.
+        // The producers never take part - they start their descriptor chain at once.  A small share (the usual case: a few KB
+        // per block) is put by the REST warp alone, four independent 16-byte pieces per lane in flight, so that the consumers
+        // start multiplying as soon as the first chunk has landed; only a large share is spread over the consumer warps too,
+        // which then meet at a named barrier behind the system fence.  (Round-2 traces, profiles/r02_trace_n2_*.txt: with all
+        // warps putting behind a block-wide barrier the first chunk was consumed 15 us after the block started, with the
+        // consumers putting 9.7 us, the producers alone need 6.)
+        constexpr unsigned NPUT = (K + 1) * 32;
         const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-        const unsigned tid = threadIdx.x - PW * 32;
         const unsigned vpr = a.put_row_bytes / 16u;
         const size_t total = (size_t) a.put_nrow * vpr;
-        for (size_t t = (size_t) bid * NPUT + tid; t < total; t += (size_t) nblocks * NPUT)
-        {
+        const bool by_all = total > (size_t) nblocks * 2048;            // more than 32 KB per block
+        auto piece_src = [&](const size_t t) -> const uint4 * {
             const unsigned r = (unsigned) (t / vpr), v = (unsigned) (t - (size_t) r * vpr);
-            const uint4 val = *reinterpret_cast<const uint4 *>(a.X0 + (size_t) a.put_ridx[r] * a.ldx0 + (size_t) v * 16);
-            *reinterpret_cast<uint4 *>(a.put_dst_rows[r] + a.put_dst_off + (size_t) v * 16) = val;
-        }
-        __threadfence_system();
-        asm volatile("bar.sync 1, %0;" :: "r"(NPUT) : "memory");          // the putting warps only
-        if (tid == 0)
+            return reinterpret_cast<const uint4 *>(a.X0 + (size_t) a.put_ridx[r] * a.ldx0 + (size_t) v * 16);
+        };
+        auto piece_dst = [&](const size_t t) -> uint4 * {
+            const unsigned r = (unsigned) (t / vpr), v = (unsigned) (t - (size_t) r * vpr);
+            return reinterpret_cast<uint4 *>(a.put_dst_rows[r] + a.put_dst_off + (size_t) v * 16);
+        };
+        if (by_all || warp == PW + K)
         {
-            if (atomicAdd(a.put_counter, 1u) == nblocks - 1u)
+            const unsigned nthr = by_all ? NPUT : 32u;
+            const unsigned tid = by_all ? threadIdx.x - PW * 32 : (unsigned) lane;
+            const size_t stride = (size_t) nblocks * nthr;
+            for (size_t t = (size_t) bid * nthr + tid; t < total; t += 4 * stride)
             {
-                __threadfence();                // the other blocks' stores (fenced before their atomicAdd) come before the flags
-                for (int j = 0; j < a.put_nflag; j++)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.put_flag_ptrs[j]), "r"(a.epoch) : "memory");
-                *a.put_counter = 0u;
+                uint4 v4[4];
+                #pragma unroll
+                for (int j = 0; j < 4; j++) if (t + j * stride < total) v4[j] = *piece_src(t + j * stride);
+                #pragma unroll
+                for (int j = 0; j < 4; j++) if (t + j * stride < total) *piece_dst(t + j * stride) = v4[j];
             }
-            if (a.trace != NULL) a.trace[(size_t) bid * 8 + 1] = gtime_ns();    // this block's share of the put is done (and counted)
+            __threadfence_system();
+            if (by_all) asm volatile("bar.sync 1, %0;" :: "r"(NPUT) : "memory");        // the putting warps only
+            else __syncwarp();
+            if (tid == 0)
+            {
+                if (atomicAdd(a.put_counter, 1u) == nblocks - 1u)
+                {
+                    __threadfence();            // the other blocks' stores (fenced before their atomicAdd) come before the flags
+                    for (int j = 0; j < a.put_nflag; j++)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.put_flag_ptrs[j]), "r"(a.epoch) : "memory");
+                    *a.put_counter = 0u;
+                }
+                if (a.trace != NULL) a.trace[(size_t) bid * 8 + 1] = gtime_ns();        // this block's share of the put is done (and counted)
+            }
         }
     }
 
