@@ -100,6 +100,7 @@ struct crp_rp_dev
     void    *stream_in, *stream_out;
     void    *ev_in[CRP_E2E_MAX_PANELS], *ev_out[CRP_E2E_MAX_PANELS];
     int     e2e_panels;         /* panels of the last pipelined exec (0: the last exec was not pipelined) */
+    int     e2e_multi_ok;       /* agreed at init: every rank of comm can cut a host-buffer exec into panel rounds */
 };
 
 /* rp_spmm_init with an explicit NCCL parent: the exchange runs on the NCCL

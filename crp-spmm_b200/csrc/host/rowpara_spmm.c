@@ -475,6 +475,13 @@ static void rp_build_device_state(rp_spmm_p rp, const int *B_row_displs, MPI_Com
     if (d->p2p) d->p2p = rp_p2p_setup(rp, d);
     if (!d->p2p) d->p2p_hostsync = 0;
     if (!d->p2p && shared_gpu) d->staged = 1;
+    /* host-buffer pipelining across ranks (rp_e2e_panel_count): possible only if every rank runs the fused peer-memory route and
+     * has rows of A and of B (an empty rank could not tell host from device buffers) - agreed once, here */
+    {
+        int mine = (nproc == 1) ? 1 : ((d->p2p && !d->overlap && !d->p2p_hostsync && rp->A_nrow > 0 && d->nB > 0) ? 1 : 0), all = mine;
+        if (nproc > 1) MPI_Allreduce(&mine, &all, 1, MPI_INT, MPI_MIN, rp->comm);
+        d->e2e_multi_ok = all;
+    }
     /* NCCL for the exchange: creating the communicator is collective over nccl_parent (the whole grid), the peer-memory
      * decision above was taken per grid column - so every member learns whether ANY column needs NCCL and joins the creation */
     int need_nccl = (nproc > 1 && !d->staged && !d->p2p) ? 1 : 0, any_nccl = need_nccl;
@@ -698,14 +705,12 @@ static int rp_e2e_panel_count(rp_spmm_p rp, struct crp_rp_dev *d, const int BC_l
     while (P > 1 && n / P < 32) P--;
     /* panels start on 64-byte boundaries: multiples of 8 columns */
     int ok = (P > 1) && BC_layout == 0 && !B_on_dev && !C_on_dev && rp->A_nrow > 0 && d->nB > 0 && (n % 8 == 0);
-    if (rp->nproc > 1)
-    {
-        /* every rank must cut the call the same way (each panel is an exchange round); only the fused peer-memory route */
-        ok = ok && d->p2p && !d->overlap && !d->p2p_hostsync && ((size_t) elem_size * (size_t) n) % 16 == 0;
-        int all = 0;
-        MPI_Allreduce(&ok, &all, 1, MPI_INT, MPI_MIN, rp->comm);
-        ok = all;
-    }
+    /* Several ranks: every rank must cut the call the same way (each panel is an exchange round).  Whether the engine CAN do it
+     * (fused peer-memory route on every rank, no rank with an empty block) was agreed once at init (e2e_multi_ok); the rest of the
+     * condition is the same on every rank as long as all of them pass the same kind of buffers (host or device) to a collective
+     * exec - which the reference's API implies (host only) and include/crp_ext.h now states.  No communication here: a host
+     * collective per exec between the start event and the launch cost 30 us of GPU idle time at 8 ranks (profiles/r02_trace_n8.txt). */
+    if (rp->nproc > 1) ok = ok && d->e2e_multi_ok && ((size_t) elem_size * (size_t) n) % 16 == 0;
     return ok ? P : 0;
 }
 

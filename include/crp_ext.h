@@ -53,6 +53,10 @@ void rp_spmm_plan_info(rp_spmm_p rp_spmm, long long out[12]);
  * (or print_stat / clear_stat) is called. */
 void rp_spmm_sync_stats(rp_spmm_p rp_spmm);
 
+/* B and C may be device pointers (zero copy) or host pointers (staged through the GPU in CRP_SPMM_E2E_PANELS column panels that
+ * pipeline H2D, exchange + product and D2H).  In a collective exec every rank must pass the SAME kind of buffers: the ranks cut the
+ * call into the same number of exchange rounds without talking to each other. */
+
 /* Host B / C buffers are cudaHostRegister'ed only with CRP_SPMM_PIN_HOST=1 (they must then outlive the engine);
  * this drops every registration made so far (also done by rp_spmm_free). */
 void crp_unpin_host_all(void);
