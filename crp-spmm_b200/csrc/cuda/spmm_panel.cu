@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
         const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
         const unsigned vpr = a.put_row_bytes / 16u;
         const size_t total = (size_t) a.put_nrow * vpr;
-        const bool by_all = total > (size_t) nblocks * 2048;            // more than 32 KB per block
+        // more than 2 KB per block: spread over the consumer warps too.  (N = 8 trace, profiles/r02_trace_n8.txt: the rest warp alone
+        // needed 30 - 42 us for 11.6 KB per block, so the flags reached the neighbours after their consumers had finished, and their
+        // rest warps - which wait for every flag before they multiply the rows at the slice boundaries - ended the kernel late.)
+        const bool by_all = total > (size_t) nblocks * 128;
         auto piece_src = [&](const size_t t) -> const uint4 * {
             const unsigned r = (unsigned) (t / vpr), v = (unsigned) (t - (size_t) r * vpr);
             return reinterpret_cast<const uint4 *>(a.X0 + (size_t) a.put_ridx[r] * a.ldx0 + (size_t) v * 16);
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
             __syncwarp();
         }
         constexpr int UT = W / (32 * VEC);                  // this warp covers the block's whole column slice
-        constexpr int NZ = 4;
+        constexpr int NZ = (UT * VEC * (int) sizeof(T) <= 32) ? 8 : 4;     // nonzeros in flight (register budget: NZ * UT * VEC values)
         const T *X0 = reinterpret_cast<const T *>(a.X0) + col0 + lane * VEC;
         const T *X1 = reinterpret_cast<const T *>(a.X1) + col0 + lane * VEC;
         const size_t ld0 = a.ldx0 / sizeof(T), ld1 = a.ldx1 / sizeof(T);
