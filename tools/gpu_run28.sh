@@ -1,6 +1,6 @@
 # round 2 session 2, run 13 (1 GPU): final validation of HEAD - whole -m gpu suite, default bench line, e2e panel shape A/B, ncu launch list
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -m gpu -q --tb=short --timeout 300 2>&1 | tail -n 15 ) > gpurun_out/r2s2_pytest_gpu_final.log
+( timeout 900 python -m pytest tests -m gpu -q --tb=short --timeout 400 -n 4 2>&1 | tail -n 15 ) > gpurun_out/r2s2_pytest_gpu_final.log
 tail -n 5 gpurun_out/r2s2_pytest_gpu_final.log
 timeout 600 python bench.py > gpurun_out/r2s2_bench_final_n1.json 2> gpurun_out/r2s2_bench_final_n1.err; echo "bench rc=$?"
 python - <<PY
