@@ -163,7 +163,15 @@ __device__ __forceinline__ long long gtime_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define CRP_TRACE(slot) do { if (a.trace != NULL && lane == 0) a.trace[(size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime_ns(); } while (0)
+// Per-block time stamps are a development aid compiled in only with -DCRP_PANEL_TRACE_BUILD (make CRP_NVCC_EXTRA=-DCRP_PANEL_TRACE_BUILD):
+// the hooks cost two instructions in the consumers' entry loop through register allocation (141 instead of 139), about 2 % of the
+// headline kernel.  The traces under profiles/r02_trace_*.txt were taken with such a build.
+#ifdef CRP_PANEL_TRACE_BUILD
+#define CRP_TRACE_ON(a) ((a).trace != NULL)
+#else
+#define CRP_TRACE_ON(a) false
+#endif
+#define CRP_TRACE(slot) do { if (CRP_TRACE_ON(a) && lane == 0) a.trace[(size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime_ns(); } while (0)
 
 template <typename T>
 struct panel_args
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
                         asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.put_flag_ptrs[j]), "r"(a.epoch) : "memory");
                     *a.put_counter = 0u;
                 }
-                if (a.trace != NULL) a.trace[(size_t) bid * 8 + 1] = gtime_ns();        // this block's share of the put is done (and counted)
+                if (CRP_TRACE_ON(a)) a.trace[(size_t) bid * 8 + 1] = gtime_ns();        // this block's share of the put is done (and counted)
             }
         }
     }
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
                 need &= ~seen;
                 if (need)
                 {
-                    const long long tw0 = (a.trace != NULL) ? gtime_ns() : 0;
+                    const long long tw0 = CRP_TRACE_ON(a) ? gtime_ns() : 0;
                     // one lane per missing neighbour spins on its arrival flag; the rows were written by the peer's stores
                     // before the flag (fence + st.release.sys on the sender)
                     if (lane < a.nwait && ((need >> lane) & 1u))
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
                     __syncwarp();
                     asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy acquire -> async-proxy (TMA) reads
                     seen |= need;
-                    if (warp == 0 && a.trace != NULL && lane == 0)
+                    if (warp == 0 && CRP_TRACE_ON(a) && lane == 0)
                     {
                         const size_t tb = (size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8;
                         a.trace[tb + 4] += gtime_ns() - tw0;                    // time this producer spent waiting for flags
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
                 }
             }
             mbar_wait(&empty[s], ph);
-            if (warp == 0 && a.trace != NULL && lane == 0)
+            if (warp == 0 && CRP_TRACE_ON(a) && lane == 0)
             {
                 const size_t tb = (size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8;
                 if (a.trace[tb + 2] == 0) a.trace[tb + 2] = gtime_ns();         // first chunk issued
@@ -561,7 +569,7 @@ __global__ void __launch_bounds__(panel_layout<K>::THREADS, 1) spmm_panel_kernel
     for (;; s = (s + 1 == nstage) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u)
     {
         mbar_wait(&full[s], ph);
-        if (w == 0 && a.trace != NULL && lane == 0)
+        if (w == 0 && CRP_TRACE_ON(a) && lane == 0)
         {
             const size_t tb = (size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8;
             if (a.trace[tb + 3] == 0) a.trace[tb + 3] = gtime_ns();             // first chunk landed
@@ -936,11 +944,14 @@ bool crp_launch_panel(
         a.put_counter = put->counter;  a.epoch = put->epoch;  a.put_dst_off = put->dst_off;
     }
     {
-        // development aid: CRP_PANEL_TRACE=<file prefix> records 8 time stamps per block of every launch (the last one is
-        // written to <prefix>.<pid> when the plan is destroyed); costs a few predicated stores, off by default
+        // development aid (builds with -DCRP_PANEL_TRACE_BUILD only): CRP_PANEL_TRACE=<file prefix> records 8 time stamps per block
+        // of every launch (the last one is written to <prefix>.<pid> when the plan is destroyed)
         static long long *d_trace = NULL;
         static int trace_on = -1;
         if (trace_on < 0) { const char *e = getenv("CRP_PANEL_TRACE"); trace_on = (e && e[0]) ? 1 : 0; }
+#ifndef CRP_PANEL_TRACE_BUILD
+        if (trace_on == 1) { fprintf(stderr, "[crpspmm] CRP_PANEL_TRACE is set but this library was built without -DCRP_PANEL_TRACE_BUILD: no trace\n"); trace_on = 0; }
+#endif
         if (trace_on)
         {
             if (d_trace == NULL) CRP_CUDA_CHECK(cudaMalloc((void **) &d_trace, sizeof(long long) * 8 * 1024));
