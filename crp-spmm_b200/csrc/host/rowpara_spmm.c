@@ -756,12 +756,13 @@ void rp_spmm_exec_any(rp_spmm_p rp, const int BC_layout, const void *B, const in
         grow_dev(&d->d_Bwork, &d->Bwork_bytes, row_bytes * (size_t) nB);
         grow_dev(&d->d_Cwork, &d->Cwork_bytes, row_bytes * (size_t) m);
         if (d->p2p) rp_p2p_tables(rp, d, elem_size);
-        /* panel boundaries: equal panels except the LAST, which is about half as wide - what follows the last H2D (its
-         * product and its D2H) is the only part of the call that nothing hides.  Multiples of 8 columns (64-byte segments). */
+        /* panel boundaries: equal panels, multiples of 8 columns (64-byte segments).  CRP_SPMM_E2E_TAPER=1 makes the last panel
+         * about half as wide (what follows the last H2D - its product and its D2H - is the only part nothing hides); measured on
+         * B200 it LOSES (14.1 vs 11.6 ms at n = 256: three 576-byte and one 320-byte segment per row copy worse than four of 512). */
         int pcol[CRP_E2E_MAX_PANELS + 1];
         {
             static int taper = -1;
-            if (taper < 0) GET_ENV_INT_VAR(taper, "CRP_SPMM_E2E_TAPER", "e2e_taper", 1, 0, 1, 0);
+            if (taper < 0) GET_ENV_INT_VAR(taper, "CRP_SPMM_E2E_TAPER", "e2e_taper", 0, 0, 1, 0);
             int base = taper ? (int) ((2ll * n) / (2 * npanel - 1)) : (n + npanel - 1) / npanel;
             base = taper ? base / 8 * 8 : (base + 7) / 8 * 8;
             if (base < 8) base = 8;
