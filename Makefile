@@ -30,8 +30,8 @@ all: lib
 
 lib: $(LIBDIR)/libminimpi.so $(BINDIR)/minimpirun $(LIBDIR)/libcrpspmm.so $(LIBDIR)/libcrpingest.so
 
-$(LIBDIR)/libcrpingest.so: $(SRC)/ingest/mmio_fast.c | $(LIBDIR)
-	$(CC) -O3 -g -std=gnu11 -fPIC -fopenmp -Wall -shared -o $@ $<
+$(LIBDIR)/libcrpingest.so: $(SRC)/ingest/mmio_fast.c $(SRC)/ingest/graph_part.c $(SRC)/ingest/metis.h | $(LIBDIR)
+	$(CC) -O3 -g -std=gnu11 -fPIC -fopenmp -Wall -I$(SRC)/ingest -shared -o $@ $(SRC)/ingest/mmio_fast.c $(SRC)/ingest/graph_part.c
 
 $(OBJDIR) $(LIBDIR) $(BINDIR):
 	mkdir -p $@
@@ -55,11 +55,12 @@ $(LIBDIR)/libcrpspmm.so: $(OBJS) $(LIBDIR)/libminimpi.so
 	$(NVCC) -shared -o $@ $(OBJS) -L$(LIBDIR) -lminimpi -ldl -lgomp -Xlinker -rpath='$$ORIGIN'
 
 # ---- the reference's own drivers against this library (drop-in check) ----
-DRV_INC  := -I$(ROOT)/include -I$(MINIMPI) -I$(ROOT)/oracle/stubs -I$(REF)/examples
+DRV_INC  := -I$(ROOT)/include -I$(MINIMPI) -I$(SRC)/ingest -I$(ROOT)/oracle/stubs -I$(REF)/examples
 # the drivers' matrix reader (mm_read_sparse_RPI + coo2csr of examples/mmio_utils.c) is replaced by the fast ingest library
-# (same signatures and results: csrc/ingest/mmio_fast.c, tests/test_ingest.py); everything else is the reference's source
+# (same signatures and results: csrc/ingest/mmio_fast.c, tests/test_ingest.py) and METIS, which the reference links but does not
+# vendor, by the native partitioner behind METIS's two entry points (csrc/ingest/graph_part.c); everything else is the reference's source
 DRV_HELP := mmio.c test_utils.c metis_mat_part.c
-DRV_OBJS := $(addprefix $(OBJDIR)/drv_,$(DRV_HELP:.c=.o)) $(OBJDIR)/drv_mkl_standin.o $(OBJDIR)/drv_metis_stub.o
+DRV_OBJS := $(addprefix $(OBJDIR)/drv_,$(DRV_HELP:.c=.o)) $(OBJDIR)/drv_mkl_standin.o
 DRV_CFLAGS := -O3 -march=x86-64-v3 -fopenmp -std=gnu11 -g -DUSE_MKL -Wno-unused-result
 
 ifneq ($(wildcard $(REF)/examples/test_para2d_spmm.c),)
@@ -76,8 +77,6 @@ $(OBJDIR)/drv_test_crpspmm.o: $(REF)/deprecated/examples/test_crpspmm.c | $(OBJD
 	$(CC) $(DRV_CFLAGS) $(DRV_INC) -c $< -o $@
 $(OBJDIR)/drv_mkl_standin.o: $(ROOT)/oracle/stubs/mkl_standin.c | $(OBJDIR)
 	$(CC) $(DRV_CFLAGS) -ffp-contract=off $(DRV_INC) -c $< -o $@
-$(OBJDIR)/drv_metis_stub.o: $(ROOT)/oracle/stubs/metis_stub.c | $(OBJDIR)
-	$(CC) $(DRV_CFLAGS) $(DRV_INC) -c $< -o $@
 
 $(BINDIR)/%.exe: $(OBJDIR)/drv_%.o $(DRV_OBJS) $(LIBDIR)/libcrpspmm.so $(LIBDIR)/libcrpingest.so | $(BINDIR)
 	$(CC) -fopenmp -o $@ $< $(DRV_OBJS) -L$(LIBDIR) -lcrpspmm -lcrpingest -lminimpi -lm -Wl,-rpath,'$$ORIGIN/../lib'

@@ -1,0 +1,164 @@
+/*
+ * graph_part.c - a native k-way graph partitioner behind the two METIS 5 entry points the reference's
+ * driver front-end calls (examples/metis_mat_part.c:31-113: METIS_SetDefaultOptions + METIS_PartGraphKway
+ * with METIS_OBJTYPE_VOL, one constraint, 5 % imbalance).  METIS itself is an un-vendored dependency of
+ * the reference (examples/makefile:4) and is not available here; with this file in libcrpingest.so the
+ * drivers' <part-method> = 1 path runs instead of aborting.  The partitions are NOT METIS's - no parity
+ * is claimed or possible without METIS - they are valid, balanced and communication-aware:
+ *
+ *   1. every connected component is ordered by a breadth-first sweep from a pseudo-peripheral vertex
+ *      (two BFS passes: the last vertex of the first is the root of the second), neighbours in
+ *      ascending degree - the Cuthill-McKee order, which keeps mesh neighbours close;
+ *   2. the order is cut into nparts contiguous pieces of equal vertex weight;
+ *   3. boundary refinement: a few sweeps move a boundary vertex to the part that holds most of its
+ *      neighbours when that reduces the edge cut and both parts stay within the imbalance bound
+ *      (deterministic: vertices in ascending id, strict improvement only).
+ * *objval returns the total communication volume (METIS_OBJTYPE_VOL: for every vertex the number of
+ * OTHER parts among its neighbours) or the edge cut (METIS_OBJTYPE_CUT).
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "metis.h"
+
+int METIS_SetDefaultOptions(idx_t *options)
+{
+    for (int i = 0; i < METIS_NOPTIONS; i++) options[i] = -1;
+    return METIS_OK;
+}
+
+/* BFS from root over the vertices with comp[v] == -1; writes the visiting order, returns the count; neighbours of a vertex are
+ * appended in ascending degree (insertion sort: degrees are small) */
+static int bfs_order(const idx_t *xadj, const idx_t *adjncy, const int root, const int comp_id, int *comp, int *order)
+{
+    int head = 0, tail = 0;
+    order[tail++] = root;
+    comp[root] = comp_id;
+    while (head < tail)
+    {
+        const int v = order[head++];
+        const int first = tail;
+        for (idx_t p = xadj[v]; p < xadj[v + 1]; p++)
+        {
+            const int u = adjncy[p];
+            if (u == v || comp[u] != -1) continue;
+            comp[u] = comp_id;
+            const int du = xadj[u + 1] - xadj[u];
+            int q = tail++;
+            while (q > first && (xadj[order[q - 1] + 1] - xadj[order[q - 1]]) > du) { order[q] = order[q - 1]; q--; }
+            order[q] = u;
+        }
+    }
+    return tail;
+}
+
+int METIS_PartGraphKway(
+    idx_t *nvtxs, idx_t *ncon, idx_t *xadj, idx_t *adjncy, idx_t *vwgt, idx_t *vsize,
+    idx_t *adjwgt, idx_t *nparts, real_t *tpwgts, real_t *ubvec, idx_t *options,
+    idx_t *objval, idx_t *part
+)
+{
+    (void) vsize; (void) adjwgt; (void) tpwgts;
+    const int n = *nvtxs, k = *nparts;
+    if (n < 0 || k < 1 || (ncon != NULL && *ncon != 1)) return -2;            /* METIS_ERROR_INPUT */
+    if (n == 0) { if (objval) *objval = 0; return METIS_OK; }
+    const double ub = (ubvec != NULL && *ubvec > 1.0) ? (double) *ubvec : 1.03;
+    const int want_vol = (options != NULL && options[METIS_OPTION_OBJTYPE] == METIS_OBJTYPE_VOL);
+
+    /* ---- 1. Cuthill-McKee order, component by component ---- */
+    int *order = (int *) malloc(sizeof(int) * (size_t) n), *tmp = (int *) malloc(sizeof(int) * (size_t) n);
+    int *comp = (int *) malloc(sizeof(int) * (size_t) n);
+    if (!order || !tmp || !comp) { free(order); free(tmp); free(comp); return -3; }     /* METIS_ERROR_MEMORY */
+    for (int v = 0; v < n; v++) comp[v] = -1;
+    int done = 0, ncomp = 0;
+    for (int s = 0; s < n; s++)
+    {
+        if (comp[s] != -1) continue;
+        /* first sweep finds a far vertex, second sweep (from it) is the order that is kept */
+        const int cnt = bfs_order(xadj, adjncy, s, ncomp, comp, tmp);
+        const int far = tmp[cnt - 1];
+        for (int i = 0; i < cnt; i++) comp[tmp[i]] = -1;
+        bfs_order(xadj, adjncy, far, ncomp, comp, order + done);
+        done += cnt;
+        ncomp++;
+    }
+    free(tmp);
+
+    /* ---- 2. contiguous pieces of equal weight ---- */
+    long long wtot = 0;
+    for (int v = 0; v < n; v++) wtot += vwgt ? vwgt[v] : 1;
+    long long *pw = (long long *) calloc((size_t) k, sizeof(long long));
+    {
+        long long acc = 0;
+        int p = 0;
+        for (int i = 0; i < n; i++)
+        {
+            const int v = order[i];
+            const long long w = vwgt ? vwgt[v] : 1;
+            /* move to the next part when this one has reached its share of what is left */
+            while (p < k - 1 && acc + w / 2 >= (wtot * (p + 1)) / k) p++;
+            part[v] = p;
+            pw[p] += w;
+            acc += w;
+        }
+    }
+    free(order);
+    free(comp);
+
+    /* ---- 3. boundary refinement ---- */
+    const double cap = ub * (double) wtot / (double) k + 1.0;
+    int *cnt = (int *) calloc((size_t) k, sizeof(int));
+    for (int sweep = 0; sweep < 8; sweep++)
+    {
+        int moved = 0;
+        for (int v = 0; v < n; v++)
+        {
+            const int pv = part[v];
+            int boundary = 0;
+            for (idx_t p = xadj[v]; p < xadj[v + 1]; p++) if (adjncy[p] != v && part[adjncy[p]] != pv) { boundary = 1; break; }
+            if (!boundary) continue;
+            for (idx_t p = xadj[v]; p < xadj[v + 1]; p++) if (adjncy[p] != v) cnt[part[adjncy[p]]]++;
+            int best = pv;
+            const long long w = vwgt ? vwgt[v] : 1;
+            for (idx_t p = xadj[v]; p < xadj[v + 1]; p++)
+            {
+                const int q = part[adjncy[p]];
+                if (adjncy[p] == v || q == pv) continue;
+                if (cnt[q] > cnt[best] && (double) (pw[q] + w) <= cap && pw[pv] - w > 0) best = q;
+            }
+            for (idx_t p = xadj[v]; p < xadj[v + 1]; p++) cnt[part[adjncy[p]]] = 0;
+            if (best != pv)
+            {
+                part[v] = best;
+                pw[pv] -= w;
+                pw[best] += w;
+                moved++;
+            }
+        }
+        if (moved == 0) break;
+    }
+
+    /* ---- objective ---- */
+    if (objval != NULL)
+    {
+        long long obj = 0;
+        int *seen = cnt;                 /* reuse: stamp per part */
+        for (int q = 0; q < k; q++) seen[q] = -1;
+        for (int v = 0; v < n; v++)
+        {
+            for (idx_t p = xadj[v]; p < xadj[v + 1]; p++)
+            {
+                const int u = adjncy[p], q = part[u];
+                if (u == v || q == part[v]) continue;
+                if (want_vol) { if (seen[q] != v) { seen[q] = v; obj++; } }
+                else if (u > v) obj++;
+            }
+        }
+        *objval = (idx_t) (obj > INT32_MAX ? INT32_MAX : obj);
+    }
+    free(cnt);
+    free(pw);
+    return METIS_OK;
+}
