@@ -218,6 +218,9 @@ static int rp_p2p_setup(rp_spmm_p rp, struct crp_rp_dev *d)
 {
     const int nproc = rp->nproc, me = rp->my_rank, n = rp->glb_n;
     int ok = (nproc <= CRP_P2P_HDR / (int) sizeof(unsigned int)) ? 1 : 0;
+    if (!ok && me == 0)
+        WARNING_PRINTF("peer-memory transport: %d ranks exceed the %d arrival flags of the header; the B-row exchange uses NCCL\n",
+                       nproc, CRP_P2P_HDR / (int) sizeof(unsigned int));
     d->p2p_half_bytes = (((size_t) d->n_recv_rows * (size_t) n * sizeof(double)) + 255) & ~(size_t) 255;
     crp_cuda_malloc_dev(&d->p2p_mem, CRP_P2P_HDR + 2 * d->p2p_half_bytes);
     crp_cuda_memset_dev(d->p2p_mem, 0, CRP_P2P_HDR);

@@ -15,13 +15,13 @@ from util import run_flow
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n,f32", [(256, False), (200, False), (384, True), (64, False)])
+@pytest.mark.parametrize("n,f32", [(256, False), (200, False), (384, True)])
 def test_panels_are_bitwise_neutral(n, f32, tmp_path):
     m, k, rp, ci, v = gen.pwtk_like(m=6000, target_nnz=316000, bandwidth=5000, grid_w=16, seed=3)
     csr = os.path.join(str(tmp_path), "a.bin")
     gen.write_csr_bin(csr, m, k, rp, ci, v)
     ref = run_flow(tmp_path, csr, n, "2d", 1, device=True, f32=f32)[0]["C"]
-    for panels in ("1", "2", "4", "7"):
+    for panels in ("1", "4", "7"):
         out = run_flow(tmp_path, csr, n, "2d", 1, device=False, f32=f32, extra_env={"CRP_SPMM_E2E_PANELS": panels})[0]
         assert np.array_equal(out["C"], ref), panels
     assert np.isfinite(ref).all() and np.abs(ref).max() > 0

@@ -187,8 +187,13 @@ def test_host_in_host_out_proxy_call(mats):
 
 
 # ---- the whole engine on P ranks (sharing this box's GPU: host-staged exchange) vs the reference's golden C ----
-@pytest.mark.parametrize("case", cases.SPMM_CASES, ids=[c[0] for c in cases.SPMM_CASES])
-@pytest.mark.parametrize("device", [False, True], ids=["hostBC", "devBC"])
+# host buffers (the reference's calling convention) for every golden case, device-resident buffers for one case per shape / flow
+DEV_CASES = {"tridiag16_2d_np8_n64", "rand300_2d_np1_n16", "rand300_2d_np4_n16_cm", "rand300_2d_np6_n24", "rand300_rp_np4_n8_noreidx",
+             "rect350x200_2d_np6_n32", "stencil6_2d_np8_n32", "rmat8_rp_np4_n16", "pwtk600_2d_np8_n64", "blockdiag_rp_np4_n8"}
+ENGINE_RUNS = [(c, False) for c in cases.SPMM_CASES] + [(c, True) for c in cases.SPMM_CASES if c[0] in DEV_CASES]
+
+
+@pytest.mark.parametrize("case,device", ENGINE_RUNS, ids=[f"{c[0]}-{'devBC' if d else 'hostBC'}" for c, d in ENGINE_RUNS])
 def test_engine_matches_reference_golden(case, device, tmp_path):
     name, spec, n, mode, nproc, layout, reidx = case
     g = dict(np.load(os.path.join(GOLD, name + ".npz")))
