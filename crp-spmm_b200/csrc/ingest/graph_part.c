@@ -9,7 +9,8 @@
  *   1. every connected component is ordered by a breadth-first sweep from a pseudo-peripheral vertex
  *      (two BFS passes: the last vertex of the first is the root of the second), neighbours in
  *      ascending degree - the Cuthill-McKee order, which keeps mesh neighbours close;
- *   2. the order is cut into nparts contiguous pieces of equal vertex weight;
+ *   2. the order is cut into nparts contiguous pieces of nearly equal vertex weight, every cut at the position
+ *      with the fewest crossing edges inside the window the imbalance bound allows;
  *   3. boundary refinement: a few sweeps move a boundary vertex to the part that holds most of its
  *      neighbours when that reduces the edge cut and both parts stay within the imbalance bound
  *      (deterministic: vertices in ascending id, strict improvement only).
@@ -86,23 +87,52 @@ int METIS_PartGraphKway(
     }
     free(tmp);
 
-    /* ---- 2. contiguous pieces of equal weight ---- */
+    /* ---- 2. contiguous pieces of (nearly) equal weight, cut where few edges cross ----
+     * crossing[i] = edges between order[0 .. i) and order[i .. n): +1 over (a, b] for every edge whose ends sit at positions
+     * a < b of the order.  Each of the k - 1 cuts may move inside the window the imbalance bound allows around its ideal
+     * position and takes the position with the fewest crossing edges (ties: closest to the ideal) - on a level-structured order
+     * that is a level boundary instead of the middle of a level. */
     long long wtot = 0;
     for (int v = 0; v < n; v++) wtot += vwgt ? vwgt[v] : 1;
     long long *pw = (long long *) calloc((size_t) k, sizeof(long long));
     {
-        long long acc = 0;
-        int p = 0;
-        for (int i = 0; i < n; i++)
+        int *pos = comp;                                    /* reuse: position of every vertex in the order */
+        for (int i = 0; i < n; i++) pos[order[i]] = i;
+        int *crossing = (int *) calloc((size_t) n + 2, sizeof(int));
+        long long *wacc = (long long *) malloc(sizeof(long long) * ((size_t) n + 1));
+        for (int v = 0; v < n; v++)
+            for (idx_t p = xadj[v]; p < xadj[v + 1]; p++)
+            {
+                const int u = adjncy[p];
+                if (pos[u] <= pos[v]) continue;             /* every undirected edge once (the graph stores both directions) */
+                crossing[pos[v] + 1]++;
+                crossing[pos[u] + 1]--;
+            }
+        for (int i = 1; i <= n; i++) crossing[i] += crossing[i - 1];
+        wacc[0] = 0;
+        for (int i = 0; i < n; i++) wacc[i + 1] = wacc[i] + (vwgt ? vwgt[order[i]] : 1);
+        /* slack per cut: half of what the bound leaves, so that two neighbouring cuts moving towards each other stay legal */
+        const double slack = 0.5 * (ub - 1.0) * (double) wtot / (double) k;
+        int prev = 0, i = 0;
+        for (int c = 1; c <= k; c++)
         {
-            const int v = order[i];
-            const long long w = vwgt ? vwgt[v] : 1;
-            /* move to the next part when this one has reached its share of what is left */
-            while (p < k - 1 && acc + w / 2 >= (wtot * (p + 1)) / k) p++;
-            part[v] = p;
-            pw[p] += w;
-            acc += w;
+            int cutpos = n;
+            if (c < k)
+            {
+                const double ideal = (double) wtot * c / k;
+                while (i < n && (double) wacc[i] < ideal) i++;
+                int best = i;
+                for (int j = i; j > prev && (double) wacc[j] >= ideal - slack; j--)
+                    if (crossing[j] < crossing[best]) best = j;
+                for (int j = i + 1; j < n && (double) wacc[j] <= ideal + slack; j++)
+                    if (crossing[j] < crossing[best]) best = j;
+                cutpos = (best > prev) ? best : prev;
+            }
+            for (int j = prev; j < cutpos; j++) { part[order[j]] = c - 1; pw[c - 1] += vwgt ? vwgt[order[j]] : 1; }
+            prev = cutpos;
         }
+        free(crossing);
+        free(wacc);
     }
     free(order);
     free(comp);
