@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise CRP_PANEL_TRACE files (one per process, written when the SpMM plan is destroyed: 8 time stamps per thread block of
-the LAST panel-kernel launch, ns relative to the earliest block start).   python tools/trace_summary.py gpurun_out/prefix.*"""
+the LAST panel-kernel launch, ns relative to the earliest block start).   python tools/trace_summary.py gpurun_out/prefix.*
+The hooks exist only in a library built with  make CRP_NVCC_EXTRA=-DCRP_PANEL_TRACE_BUILD  (they cost ~2 % of the headline kernel)."""
 import sys
 
 import numpy as np
