@@ -2,8 +2,7 @@
 """Kernel-only timing of the local SpMM variants on one GPU (development aid; bench.py is the contract).
    python tools/kbench.py [--workload pwtk] [--n 256] [--variants auto,rowsplit] [--iters 10] [--env K=V,...]
 Each variant is timed with CUDA events around single launches, L2 flushed in between.
-Variant specs may carry environment settings, e.g. auto:CRP_SPMM_RG_CFG=61 (indices 0..49 need a library built with
-CRP_NVCC_EXTRA=-DCRP_DEV_SWEEP; 60..64 are always available)."""
+Variant specs may carry environment settings, e.g. auto:CRP_PANEL_CLUSTER=0 or panel:CRP_PANEL_CR=24:CRP_PANEL_EMAX=96."""
 import argparse
 import json
 import os
